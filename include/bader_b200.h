@@ -1,0 +1,172 @@
+/*
+ * bader_b200.h -- C ABI of the B200-native Bader hot path (libbader_b200.so).
+ *
+ * This is the drop-in boundary: every entry point replaces one call that the
+ * reference's `Bader` object (pybader/interface.py) makes into its numba layer
+ * (pybader/thread_handlers.py, pybader/utils.py, pybader/methods.py,
+ * pybader/refinement.py).  The reference file:line each one stands in for is
+ * cited on the declaration.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; the message of
+ *    the last failure on the calling thread is bdr_last_error().
+ *  - there is NO CPU fallback: without a CUDA device every compute entry fails.
+ *  - arrays are C-contiguous [x][y][z], z fastest (io/vasp.py:102-103).
+ *  - host buffers are borrowed for the duration of the call only.
+ *  - labels on the device are int32: -1 vacuum, >= 0 volume number.
+ *  - dist_mat is the reference's 3x3x3 table verbatim (interface.py:242-259;
+ *    index 2 on an axis is the step -1), T_grad its 3x3 (interface.py:285-290).
+ *  - one handle = one device = one stream; calls on a handle must not overlap.
+ */
+#ifndef BADER_B200_H
+#define BADER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bdr_ctx bdr_ctx;
+
+enum { BDR_METHOD_ONGRID = 0, BDR_METHOD_NEARGRID = 1 };   /* methods.py:12 */
+enum { BDR_MODE_ALL = 0, BDR_MODE_CHANGED = 1 };           /* thread_handlers.py:201 */
+enum { BDR_RHO_REFERENCE = 0, BDR_RHO_CHARGE = 1, BDR_RHO_SPIN = 2 };
+enum { BDR_LABELS_BADER = 0, BDR_LABELS_ATOMS = 1 };
+
+/* kernel families for bdr_profile_get (CUDA-event time on the handle's stream) */
+enum {
+    BDR_K_VACUUM = 0,      /* vacuum mask + sums                      */
+    BDR_K_STENCIL = 1,     /* 27-point stencil -> ascent pointers     */
+    BDR_K_RESOLVE = 2,     /* pointer jumping to root codes           */
+    BDR_K_RELABEL = 3,     /* slot -> volume-number LUT pass          */
+    BDR_K_EDGE_FLAG = 4,   /* edge classification stencil             */
+    BDR_K_EDGE_DILATE = 5, /* near-edge dilation + compaction         */
+    BDR_K_TRACE = 6,       /* neargrid trajectory re-trace of edges   */
+    BDR_K_EDGE_CHECK = 7,  /* 'changed'-mode incremental reclassify   */
+    BDR_K_CHARGE_SUM = 8,  /* per-volume charge / voxel-count sums    */
+    BDR_K_ASSIGN = 9,      /* maxima -> atom, label -> atom LUT pass  */
+    BDR_K_SURFACE = 10,    /* min distance atom -> its surface        */
+    BDR_K_NARROW = 11,     /* int32 -> int8/16/64 staging for D2H     */
+    BDR_K_SYNTH = 12,      /* synthetic density generator             */
+    BDR_K_FIRST = 13,      /* first-voxel (numbering) pass            */
+    BDR_K_COUNT = 14
+};
+
+const char *bdr_last_error(void);
+int bdr_version(void);
+int bdr_device_count(int *count);
+
+/* ---- lifecycle ---------------------------------------------------------- */
+/* Allocates device state for an nx*ny*nz periodic grid on `device`.         */
+int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out);
+int bdr_destroy(bdr_ctx *ctx);
+int bdr_synchronize(bdr_ctx *ctx);
+
+/* ---- data movement (host <-> device) ------------------------------------ */
+/* which = BDR_RHO_*.  Bader.reference / .density / .spin (interface.py:136-137,
+ * 203-213).  Slots never uploaded alias BDR_RHO_REFERENCE.                  */
+int bdr_upload_density(bdr_ctx *ctx, int which, const double *host);
+int bdr_download_density(bdr_ctx *ctx, int which, double *host);
+/* Make slot `which` an alias of slot `of` (e.g. density is reference).      */
+int bdr_alias_density(bdr_ctx *ctx, int which, int of);
+/* Labels in/out in any of the reference's label dtypes (jits.py:9: int8/16/
+ * 32/64); elem_size in bytes.  Narrowing happens on the device
+ * (utils.dtype_change, utils.py:256-259).                                   */
+int bdr_upload_labels(bdr_ctx *ctx, int which, const void *host, int elem_size);
+int bdr_download_labels(bdr_ctx *ctx, int which, void *host, int elem_size);
+int bdr_download_known(bdr_ctx *ctx, int8_t *host);
+int bdr_clear_labels(bdr_ctx *ctx, int which);
+
+/* ---- hot path ----------------------------------------------------------- */
+/* utils.vacuum_assign (utils.py:383-401), called by Bader.volumes_init
+ * (interface.py:449-469): reference <= tol -> label -1; returns
+ * charge = (sum density)*voxel_volume and volume = count*voxel_volume.      */
+int bdr_vacuum_assign(bdr_ctx *ctx, double vac_tol, double voxel_volume,
+                      int which_density, double *vac_charge, double *vac_volume);
+
+/* thread_handlers.bader_calc (thread_handlers.py:15-75) -> methods.ongrid /
+ * methods.neargrid (methods.py:15-219, 222-611).  Consumes the BADER labels
+ * (0 = to do, -1 = vacuum) and leaves 0-based volume numbers, numbered by the
+ * first voxel (C order) of each volume like the reference's discovery order.
+ * neargrid: see DESIGN.md -- labels are the refinement fixed point.         */
+int bdr_bader_calc(bdr_ctx *ctx, int method, const double *dist_mat,
+                   const double *T_grad, int64_t *n_maxima);
+/* voxel indices of the maxima, int64[n][3] (the reference's bader_max).     */
+int bdr_get_maxima(bdr_ctx *ctx, int64_t *out, int64_t cap);
+
+/* thread_handlers.refine (thread_handlers.py:128-236) -> refinement.edge_find
+ * / refinement.neargrid / refinement.edge_check (refinement.py:326, 17, 409)
+ * on label set `which`.  iters < 0 = until nothing changes.  history receives
+ * (edges, changed) per iteration, up to hist_cap pairs; iters_run the count. */
+int bdr_refine(bdr_ctx *ctx, int which, int mode, int64_t iters,
+               const double *dist_mat, const double *T_grad,
+               int64_t *iters_run, int64_t *history, int64_t hist_cap);
+
+/* refinement.edge_find (refinement.py:326-405): fills the known array from
+ * label set `which`; returns the number of edge voxels.                     */
+int bdr_edge_find(bdr_ctx *ctx, int which, int64_t *edges);
+
+/* utils.charge_sum (utils.py:236-252), called by Bader.sum_volumes
+ * (interface.py:492-525).  charge[l] = voxel_volume * sum density,
+ * volume[l] = voxel_volume * count, for labels 0 <= l < n.                  */
+int bdr_charge_sum(bdr_ctx *ctx, int which_labels, int which_density,
+                   double voxel_volume, int64_t n, double *charge, double *volume);
+
+/* thread_handlers.assign_to_atoms (thread_handlers.py:78-125) ->
+ * utils.atom_assign (utils.py:186-232) + utils.volume_assign (utils.py:405-421):
+ * nearest atom over 27 images per maximum, then ATOMS labels = LUT(BADER).   */
+int bdr_assign_atoms(bdr_ctx *ctx, const double *maxima_cart, int64_t n_max,
+                     const double *atoms_cart, int64_t n_atoms, const double *lattice,
+                     int64_t *bader_atoms, double *bader_distance);
+
+/* thread_handlers.surface_distance (thread_handlers.py:239-297) ->
+ * refinement.edge_find + utils.surface_dist (utils.py:321-379) on label set
+ * `which` (the reference passes atoms_volumes).  found = 0 when there is no
+ * edge (the reference returns None).                                        */
+int bdr_surface_distance(bdr_ctx *ctx, int which, const double *lattice,
+                         const double *atoms_cart, int64_t n_atoms,
+                         double *distance, int *found);
+
+/* utils.volume_mask (utils.py:462-476): out = density where label == vol_num */
+int bdr_volume_mask(bdr_ctx *ctx, int which_labels, int which_density,
+                    int64_t vol_num, double *host_out);
+
+/* ---- one-shot, host buffers in / host buffers out ----------------------- */
+/* Bader.__call__ stages volumes_init -> bader_calc -> refine_volumes ->
+ * sum_volumes(bader=True) (interface.py:405-410) in one call: uploads the
+ * density, runs the device pipeline, downloads labels narrowed to
+ * label_elem_size.  vac_tol = NaN means no vacuum.  charge/volume may be
+ * NULL; maxima receives up to max_cap int64[3] rows.                         */
+int bdr_run(bdr_ctx *ctx, const double *host_density, double vac_tol,
+            double voxel_volume, int method, int refine_mode, int64_t refine_iters,
+            const double *dist_mat, const double *T_grad, void *host_labels,
+            int label_elem_size, int64_t *n_maxima, int64_t *maxima, int64_t max_cap,
+            double *charge, double *volume);
+
+/* ---- measurement --------------------------------------------------------- */
+int bdr_profile_enable(bdr_ctx *ctx, int on);
+int bdr_profile_reset(bdr_ctx *ctx);
+/* total CUDA-event milliseconds and launch count of one kernel family       */
+int bdr_profile_get(bdr_ctx *ctx, int family, double *ms, int64_t *launches);
+/* number of kernels this library launched on the handle since creation      */
+int bdr_launch_count(bdr_ctx *ctx, int64_t *launches);
+
+/* ---- synthetic inputs (bench / tests) ------------------------------------ */
+/* separable Gaussian superposition for orthorhombic cells: rho[i][j][k] =
+ * sum_a tx[a][i]*ty[a][j]*tz[a][k]; tables are host float64, amplitude folded
+ * into tx.  Writes slot `which` on the device.                              */
+int bdr_synth_separable(bdr_ctx *ctx, int which, const double *tx, const double *ty,
+                        const double *tz, int64_t n_atoms);
+/* general cell: sum over atoms and 27 images of amp*exp(-r^2/(2 sigma^2))    */
+int bdr_synth_general(bdr_ctx *ctx, int which, const double *lattice,
+                      const double *frac_atoms, const double *amps,
+                      const double *sigmas, int64_t n_atoms);
+
+/* device pointers, for torch.distributed halo plumbing in the sharded path  */
+int bdr_device_ptr(bdr_ctx *ctx, int what, void **ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,830 @@
+// bader_b200.cu -- host side of libbader_b200.so: the C ABI declared in
+// include/bader_b200.h on top of the kernels in kernels.cuh.
+#include "kernels.cuh"
+
+namespace bdr {
+thread_local std::string g_err;
+
+constexpr int TX = 8, TY = 8, TZ = 32;  // stencil tile (z fastest)
+
+static dim3 tile_grid(const Grid &g) {
+    return dim3((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + TX - 1) / TX);
+}
+static unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+static Weights make_weights(const double *dist_mat) {
+    Weights W;
+    for (int ix = -1; ix <= 1; ++ix)
+        for (int iy = -1; iy <= 1; ++iy)
+            for (int iz = -1; iz <= 1; ++iz)
+                W.w[(ix + 1) * 9 + (iy + 1) * 3 + (iz + 1)] =
+                    dist_mat[((ix + 3) % 3) * 9 + ((iy + 3) % 3) * 3 + ((iz + 3) % 3)];
+    return W;
+}
+static TGrad make_tgrad(const double *T) {
+    TGrad t;
+    for (int i = 0; i < 9; ++i) t.t[i] = T[i];
+    return t;
+}
+
+static double *rho_ptr(bdr_ctx *c, int which) {
+    int w = which;
+    for (int hop = 0; hop < 3 && c->rho_alias[w] >= 0 && c->rho[w] == nullptr; ++hop)
+        w = c->rho_alias[w];
+    return c->rho[w];
+}
+
+static int check(bdr_ctx *c) {
+    if (!c) return fail_msg("null handle");
+    CU(cudaSetDevice(c->device));
+    return 0;
+}
+
+static int ensure_labels(bdr_ctx *c, int which) {
+    if (c->labels[which]) return 0;
+    CU(cudaMalloc((void **)&c->labels[which], (size_t)c->N * sizeof(int32_t)));
+    CU(cudaMemsetAsync(c->labels[which], 0, (size_t)c->N * sizeof(int32_t), c->stream));
+    return 0;
+}
+static int ensure_known(bdr_ctx *c) {
+    if (c->known) return 0;
+    CU(cudaMalloc((void **)&c->known, (size_t)c->N));
+    return 0;
+}
+static int ensure_rho(bdr_ctx *c, int which) {
+    if (c->rho[which]) return 0;
+    CU(cudaMalloc((void **)&c->rho[which], (size_t)c->N * sizeof(double)));
+    c->rho_alias[which] = -1;
+    return 0;
+}
+static int ensure_sums(bdr_ctx *c, int64_t n) {
+    if (c->d_sums_cap >= n) return 0;
+    if (c->d_sums) cudaFree(c->d_sums);
+    c->d_sums = nullptr;
+    c->d_sums_cap = 0;
+    const int64_t cap = std::max<int64_t>(n + n / 4, 64);
+    CU(cudaMalloc((void **)&c->d_sums, (size_t)cap * sizeof(double)));
+    c->d_sums_cap = cap;
+    return 0;
+}
+static int ensure_slots(bdr_ctx *c, int64_t n) {
+    if (c->slots_cap >= n) return 0;
+    for (int32_t **p : {&c->roots, &c->minidx, &c->rank}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    c->slots_cap = 0;
+    const int64_t cap = std::max<int64_t>(n + n / 4, 4096);
+    CU(cudaMalloc((void **)&c->roots, (size_t)cap * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&c->minidx, (size_t)cap * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&c->rank, (size_t)cap * sizeof(int32_t)));
+    c->slots_cap = cap;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// numbering: volume numbers ascend with the first voxel (C order) carrying them
+// ---------------------------------------------------------------------------
+// `keys` = first voxel per current id, `n` ids.  Produces rank (id -> number)
+// on the device; returns in `order` the ids sorted by key.
+static int rank_from_first(bdr_ctx *c, int64_t n, std::vector<int32_t> &order, bool *identity) {
+    std::vector<int32_t> keys((size_t)n);
+    CU(cudaMemcpyAsync(keys.data(), c->minidx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    order.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) order[(size_t)i] = (int32_t)i;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return keys[(size_t)a] != keys[(size_t)b] ? keys[(size_t)a] < keys[(size_t)b] : a < b;
+    });
+    std::vector<int32_t> rank((size_t)n);
+    bool ident = true;
+    for (int64_t r = 0; r < n; ++r) {
+        rank[(size_t)order[(size_t)r]] = (int32_t)r;
+        ident &= (order[(size_t)r] == r);
+    }
+    if (identity) *identity = ident;
+    CU(cudaMemcpyAsync(c->rank, rank.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// ongrid: stencil -> pointer codes -> resolve -> numbering
+// ---------------------------------------------------------------------------
+static int ongrid_dev(bdr_ctx *c, const Weights &W) {
+    TRY(ensure_labels(c, BDR_LABELS_BADER));
+    TRY(ensure_slots(c, 4096));
+    const size_t smem = (size_t)(TX + 2) * (TY + 2) * (TZ + 2) * sizeof(double) +
+                       (size_t)TX * TY * TZ * sizeof(int32_t);
+    int32_t *code = c->labels[BDR_LABELS_BADER];
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        TRY(zero_counter(c, CNT_ROOTS));
+        LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<TX, TY, TZ>), tile_grid(c->g), 256, smem,
+               rho_ptr(c, BDR_RHO_REFERENCE), code, c->g, W, c->d_cnt + CNT_ROOTS, c->roots,
+               c->slots_cap);
+        TRY(read_counters(c));
+        const int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
+        if (n <= c->slots_cap) break;
+        if (attempt == 1) return fail_msg("maxima list overflow");
+        // codes are garbage beyond capacity: restore vacuum/unassigned and redo
+        // (only voxel classes -1 / not -1 matter to the stencil pass)
+        TRY(ensure_slots(c, n));
+    }
+    const int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
+    c->n_max = n;
+    c->maxima.assign((size_t)n * 3, 0);
+    if (n == 0) return 0;
+    CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
+    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 256), 256, 0, code, c->N, c->minidx);
+    std::vector<int32_t> order;
+    TRY(rank_from_first(c, n, order, nullptr));
+    std::vector<int32_t> roots((size_t)n);
+    CU(cudaMemcpyAsync(roots.data(), c->roots, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int64_t nyz = (int64_t)c->g.ny * c->g.nz;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t v = roots[(size_t)order[(size_t)r]];
+        c->maxima[(size_t)r * 3 + 0] = v / nyz;
+        c->maxima[(size_t)r * 3 + 1] = (v / c->g.nz) % c->g.ny;
+        c->maxima[(size_t)r * 3 + 2] = v % c->g.nz;
+    }
+    LAUNCH(c, BDR_K_RELABEL, k_relabel_slots, blocks_for(c->N, 256), 256, 0, code, c->N, c->rank);
+    return 0;
+}
+
+// renumber an already numbered label array by first voxel; permutes maxima too
+static int renumber_dev(bdr_ctx *c, int which) {
+    const int64_t n = c->n_max;
+    if (n == 0) return 0;
+    CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
+    LAUNCH(c, BDR_K_FIRST, k_first_voxel, blocks_for(c->N, 256), 256, 0, c->labels[which], c->N,
+           c->minidx);
+    std::vector<int32_t> order;
+    bool ident = true;
+    TRY(rank_from_first(c, n, order, &ident));
+    if (ident) return 0;
+    std::vector<int64_t> mx((size_t)n * 3);
+    for (int64_t r = 0; r < n; ++r)
+        for (int k = 0; k < 3; ++k)
+            mx[(size_t)r * 3 + k] = c->maxima[(size_t)order[(size_t)r] * 3 + k];
+    c->maxima.swap(mx);
+    LAUNCH(c, BDR_K_RELABEL, k_relabel_lut, blocks_for(c->N, 256), 256, 0, c->labels[which],
+           c->labels[which], c->N, c->rank);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// refinement pieces
+// ---------------------------------------------------------------------------
+static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges) {
+    TRY(ensure_known(c));
+    if (!c->labels[which]) return fail_msg("edge_find: label set is empty");
+    TRY(ensure(&c->list, &c->list_cap, std::max<int64_t>(c->N / 8, 1024)));
+    TRY(zero_counter(c, CNT_EDGES));
+    LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_flags<TX, TY, TZ>), tile_grid(c->g), 256, 0,
+           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->d_cnt + CNT_EDGES,
+           c->list, c->list_cap);
+    TRY(read_counters(c));
+    const int64_t n = (int64_t)c->h_cnt[CNT_EDGES];
+    if (n > c->list_cap) {
+        TRY(ensure(&c->list, &c->list_cap, n));
+        TRY(zero_counter(c, CNT_EDGES));
+        LAUNCH(c, BDR_K_EDGE_FLAG, k_compact_known, blocks_for(c->N, 256), 256, 0, c->known, c->N,
+               (int8_t)-2, c->d_cnt + CNT_EDGES, c->list, c->list_cap);
+    }
+    if (n > 0)
+        LAUNCH(c, BDR_K_EDGE_DILATE, (k_edge_dilate<TX, TY, TZ>), tile_grid(c->g), 256, 0, c->known,
+               c->g);
+    c->list_n = n;
+    *edges = n;
+    return 0;
+}
+
+// one Jacobi iteration of the trajectory re-trace over c->list[0..list_n)
+static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, int64_t *changed,
+                     bool want_changed_list) {
+    const int64_t n = c->list_n;
+    *changed = 0;
+    if (n == 0) return 0;
+    if (want_changed_list) TRY(ensure(&c->list2, &c->list2_cap, n));
+    TRY(ensure(&c->list3, &c->list3_cap, n));  // overflow list can never overflow
+    const int step_cap = 1 << 20;
+    CU(cudaMemsetAsync(c->d_cnt + CNT_CHANGED, 0, sizeof(unsigned long long) * 2, c->stream));
+    CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
+    LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n, 128), 128, 0,
+           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, W, T, c->list, n,
+           (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
+           c->list2_cap, c->list3, c->list3_cap, step_cap);
+    TRY(read_counters(c));
+    if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
+    const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
+    if (ov > 0) {
+        // long paths: redo those voxels with a path buffer in global memory,
+        // in batches so the scratch stays bounded (SLOW_CAP * 4 B per voxel)
+        constexpr int SLOW_CAP = 4096;
+        const int64_t batch = 16384;
+        TRY(ensure_stage(c, (size_t)std::min(ov, batch) * SLOW_CAP * sizeof(int32_t)));
+        CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
+        for (int64_t o = 0; o < ov; o += batch) {
+            const int64_t m = std::min(batch, ov - o);
+            LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
+                   rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, W, T,
+                   c->list3 + o, m, (int32_t *)c->stage, c->d_cnt,
+                   want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
+                   (int32_t *)nullptr, (int64_t)0, step_cap);
+        }
+        TRY(read_counters(c));
+        if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
+    }
+    *changed = (int64_t)c->h_cnt[CNT_CHANGED];
+    return 0;
+}
+
+// refinement.edge_check restated (see kernels.cuh K5).  Input: c->list2 holds
+// the voxels changed by the last trace (known == -2).  Output: c->list holds
+// the voxels to trace next (known == -2).
+static int edge_check_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *edges) {
+    *edges = 0;
+    c->list_n = 0;
+    if (n_changed == 0) return 0;
+    const double *rho = rho_ptr(c, BDR_RHO_REFERENCE);
+    const int32_t *lab = c->labels[which];
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_init, blocks_for(n_changed, 128), 128, 0, rho, lab, c->known,
+           c->g, c->list2, n_changed);
+    for (int round = 0;; ++round) {
+        TRY(zero_counter(c, CNT_UNDECIDED));
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_round, blocks_for(n_changed, 128), 128, 0, c->known, c->g,
+               c->list2, n_changed, c->d_cnt + CNT_UNDECIDED);
+        TRY(read_counters(c));
+        if (c->h_cnt[CNT_UNDECIDED] == 0) break;
+        if (round > 1 << 20) return fail_msg("edge_check: centre selection did not converge");
+    }
+    TRY(ensure(&c->list3, &c->list3_cap, n_changed));
+    TRY(zero_counter(c, CNT_CENTRES));
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_collect_centres, blocks_for(n_changed, 128), 128, 0, c->known,
+           c->list2, n_changed, c->d_cnt + CNT_CENTRES, c->list3);
+    TRY(read_counters(c));
+    const int64_t nc = (int64_t)c->h_cnt[CNT_CENTRES];
+    TRY(ensure(&c->list, &c->list_cap, nc * 27 + nc));
+    TRY(zero_counter(c, CNT_NEWEDGE));
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_classify, blocks_for(nc * 27, 128), 128, 0, rho, lab, c->known,
+           c->g, c->list3, nc, c->d_cnt + CNT_NEWEDGE, c->list, c->list_cap);
+    TRY(read_counters(c));
+    const int64_t ne = (int64_t)c->h_cnt[CNT_NEWEDGE];
+    if (ne > 0)
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_dilate, blocks_for(ne * 27, 128), 128, 0, c->known, c->g,
+               c->list, ne);
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_finish, blocks_for(ne + nc, 128), 128, 0, c->known, c->list, ne,
+           c->list3, nc, c->d_cnt + CNT_NEWEDGE, c->list_cap);
+    TRY(read_counters(c));
+    c->list_n = (int64_t)c->h_cnt[CNT_NEWEDGE];
+    *edges = ne;
+    return 0;
+}
+
+// thread_handlers.refine (thread_handlers.py:144-236)
+static int refine_dev(bdr_ctx *c, int which, int mode, int64_t iters, const Weights &W,
+                      const TGrad &T, int64_t *iters_run, int64_t *history, int64_t hist_cap) {
+    int64_t run = 0;
+    auto record = [&](int64_t e, int64_t ch) {
+        if (history && run < hist_cap) {
+            history[2 * run] = e;
+            history[2 * run + 1] = ch;
+        }
+        ++run;
+    };
+    if (iters_run) *iters_run = 0;
+    if (iters == 0) return 0;
+    int64_t edges = 0, changed = 0;
+    TRY(edge_find_dev(c, which, &edges));
+    if (edges == 0) return 0;
+    const bool chg_mode = (mode == BDR_MODE_CHANGED);
+    TRY(trace_dev(c, which, W, T, &changed, chg_mode));
+    record(edges, changed);
+    for (int64_t it = 2; iters < 0 || it <= iters; ++it) {
+        if (chg_mode) {
+            TRY(edge_check_dev(c, which, changed, &edges));
+        } else {
+            // a fresh edge_find on unchanged labels reproduces the previous
+            // iteration exactly, so it would again change nothing
+            if (changed == 0) {
+                record(edges, 0);
+                break;
+            }
+            TRY(edge_find_dev(c, which, &edges));
+        }
+        TRY(trace_dev(c, which, W, T, &changed, chg_mode));
+        record(edges, changed);
+        if (changed == 0) break;
+    }
+    if (iters_run) *iters_run = run;
+    return 0;
+}
+
+template <typename T>
+static int download_cast(bdr_ctx *c, const int32_t *src, void *host) {
+    TRY(ensure_stage(c, (size_t)c->N * sizeof(T)));
+    LAUNCH(c, BDR_K_NARROW, k_narrow<T>, blocks_for(c->N, 256), 256, 0, src, (T *)c->stage, c->N);
+    CU(cudaMemcpyAsync(host, c->stage, (size_t)c->N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+template <typename T>
+static int upload_cast(bdr_ctx *c, int32_t *dst, const void *host) {
+    TRY(ensure_stage(c, (size_t)c->N * sizeof(T)));
+    CU(cudaMemcpyAsync(c->stage, host, (size_t)c->N * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, BDR_K_NARROW, k_widen<T>, blocks_for(c->N, 256), 256, 0, (const T *)c->stage, dst,
+           c->N);
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int charge_sum_dev(bdr_ctx *c, int which_labels, int which_density, double dV, int64_t n,
+                          double *charge, double *volume) {
+    if (!c->labels[which_labels]) return fail_msg("charge_sum: label set is empty");
+    const double *dens = rho_ptr(c, which_density);
+    if (!dens) return fail_msg("charge_sum: density slot is empty");
+    if (n <= 0) return 0;
+    TRY(ensure_sums(c, 2 * n));
+    CU(cudaMemsetAsync(c->d_sums, 0, (size_t)(2 * n) * sizeof(double), c->stream));
+    double *q = c->d_sums;
+    unsigned long long *cnt = reinterpret_cast<unsigned long long *>(c->d_sums + n);
+    const int64_t per_block = 256 * 64;
+    const unsigned nb = blocks_for(c->N, (int)per_block);
+    if (n <= SUM_BINS)
+        LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<true>, nb, 256, 0, dens, c->labels[which_labels],
+               c->N, (int)n, q, cnt, per_block);
+    else
+        LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<false>, nb, 256, 0, dens, c->labels[which_labels],
+               c->N, (int)n, q, cnt, per_block);
+    std::vector<double> hq((size_t)n);
+    std::vector<unsigned long long> hc((size_t)n);
+    CU(cudaMemcpyAsync(hq.data(), q, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hc.data(), cnt, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        // the reference adds into caller-provided (zeroed) arrays, then scales
+        if (charge) charge[i] = (charge[i] + hq[(size_t)i]) * dV;
+        if (volume) volume[i] += (double)hc[(size_t)i] * dV;
+    }
+    return 0;
+}
+
+}  // namespace bdr
+
+using namespace bdr;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char *bdr_last_error(void) { return g_err.c_str(); }
+int bdr_version(void) { return 100; }
+
+int bdr_device_count(int *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail("cudaGetDeviceCount", __FILE__, __LINE__, e);
+    }
+    *count = n;
+    return 0;
+}
+
+int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out) {
+    if (!out) return fail_msg("bdr_create: null out");
+    *out = nullptr;
+    if (nx < 1 || ny < 1 || nz < 1) return fail_msg("bdr_create: empty grid");
+    const int64_t N = nx * ny * nz;
+    if (N > (int64_t)2147483647 - 65536)
+        return fail_msg("bdr_create: grid too large for one device handle (N must be < 2^31 - 2^16); shard it");
+    int ndev = 0;
+    TRY(bdr_device_count(&ndev));
+    if (ndev == 0) return fail_msg("bdr_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail_msg("bdr_create: bad device index");
+    CU(cudaSetDevice(device));
+    bdr_ctx *c = new bdr_ctx();
+    c->device = device;
+    c->g = Grid{(int)nx, (int)ny, (int)nz};
+    c->N = N;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc((void **)&c->d_cnt, sizeof(unsigned long long) * CNT_NUM));
+    CU(cudaMemsetAsync(c->d_cnt, 0, sizeof(unsigned long long) * CNT_NUM, c->stream));
+    CU(cudaMallocHost((void **)&c->h_cnt, sizeof(unsigned long long) * CNT_NUM));
+    const size_t smem = (size_t)(TX + 2) * (TY + 2) * (TZ + 2) * sizeof(double) +
+                       (size_t)TX * TY * TZ * sizeof(int32_t);
+    CU(cudaFuncSetAttribute(k_ongrid_pointers<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)smem));
+    *out = c;
+    return 0;
+}
+
+int bdr_destroy(bdr_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 3; ++i)
+        if (c->rho[i]) cudaFree(c->rho[i]);
+    for (int i = 0; i < 2; ++i)
+        if (c->labels[i]) cudaFree(c->labels[i]);
+    for (void *p : {(void *)c->known, (void *)c->list, (void *)c->list2, (void *)c->list3,
+                    (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
+                    (void *)c->d_sums, c->stage})
+        if (p) cudaFree(p);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto &r : c->recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : c->pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int bdr_synchronize(bdr_ctx *c) {
+    TRY(check(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_upload_density(bdr_ctx *c, int which, const double *host) {
+    TRY(check(c));
+    if (which < 0 || which > 2 || !host) return fail_msg("bdr_upload_density: bad argument");
+    TRY(ensure_rho(c, which));
+    CU(cudaMemcpyAsync(c->rho[which], host, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_download_density(bdr_ctx *c, int which, double *host) {
+    TRY(check(c));
+    if (which < 0 || which > 2 || !host) return fail_msg("bdr_download_density: bad argument");
+    const double *p = rho_ptr(c, which);
+    if (!p) return fail_msg("bdr_download_density: slot is empty");
+    CU(cudaMemcpyAsync(host, p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_alias_density(bdr_ctx *c, int which, int of) {
+    TRY(check(c));
+    if (which < 0 || which > 2 || of < 0 || of > 2 || which == of)
+        return fail_msg("bdr_alias_density: bad argument");
+    if (c->rho[which]) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->rho[which]);
+        c->rho[which] = nullptr;
+    }
+    c->rho_alias[which] = of;
+    return 0;
+}
+
+int bdr_clear_labels(bdr_ctx *c, int which) {
+    TRY(check(c));
+    if (which < 0 || which > 1) return fail_msg("bdr_clear_labels: bad argument");
+    TRY(ensure_labels(c, which));
+    CU(cudaMemsetAsync(c->labels[which], 0, (size_t)c->N * sizeof(int32_t), c->stream));
+    return 0;
+}
+
+int bdr_upload_labels(bdr_ctx *c, int which, const void *host, int elem_size) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !host) return fail_msg("bdr_upload_labels: bad argument");
+    TRY(ensure_labels(c, which));
+    switch (elem_size) {
+        case 1: return upload_cast<int8_t>(c, c->labels[which], host);
+        case 2: return upload_cast<int16_t>(c, c->labels[which], host);
+        case 4:
+            CU(cudaMemcpyAsync(c->labels[which], host, (size_t)c->N * 4, cudaMemcpyHostToDevice,
+                               c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            return 0;
+        case 8: return upload_cast<int64_t>(c, c->labels[which], host);
+    }
+    return fail_msg("bdr_upload_labels: elem_size must be 1, 2, 4 or 8");
+}
+
+int bdr_download_labels(bdr_ctx *c, int which, void *host, int elem_size) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !host) return fail_msg("bdr_download_labels: bad argument");
+    if (!c->labels[which]) return fail_msg("bdr_download_labels: label set is empty");
+    switch (elem_size) {
+        case 1: return download_cast<int8_t>(c, c->labels[which], host);
+        case 2: return download_cast<int16_t>(c, c->labels[which], host);
+        case 4:
+            CU(cudaMemcpyAsync(host, c->labels[which], (size_t)c->N * 4, cudaMemcpyDeviceToHost,
+                               c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            return 0;
+        case 8: return download_cast<int64_t>(c, c->labels[which], host);
+    }
+    return fail_msg("bdr_download_labels: elem_size must be 1, 2, 4 or 8");
+}
+
+int bdr_download_known(bdr_ctx *c, int8_t *host) {
+    TRY(check(c));
+    if (!c->known) return fail_msg("bdr_download_known: no edge pass has run");
+    CU(cudaMemcpyAsync(host, c->known, (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_vacuum_assign(bdr_ctx *c, double vac_tol, double voxel_volume, int which_density,
+                      double *vac_charge, double *vac_volume) {
+    TRY(check(c));
+    const double *ref = rho_ptr(c, BDR_RHO_REFERENCE);
+    const double *dens = rho_ptr(c, which_density);
+    if (!ref || !dens) return fail_msg("bdr_vacuum_assign: density not uploaded");
+    TRY(ensure_labels(c, BDR_LABELS_BADER));
+    TRY(ensure_sums(c, 2));
+    CU(cudaMemsetAsync(c->d_sums, 0, sizeof(double), c->stream));
+    TRY(zero_counter(c, CNT_VACUUM));
+    const unsigned nb = std::min<unsigned>(blocks_for(c->N, 256 * 8), 148 * 16);
+    LAUNCH(c, BDR_K_VACUUM, k_vacuum, nb, 256, 0, ref, dens, c->labels[BDR_LABELS_BADER], c->N,
+           vac_tol, c->d_sums, c->d_cnt + CNT_VACUUM);
+    double s = 0;
+    CU(cudaMemcpyAsync(&s, c->d_sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    TRY(read_counters(c));
+    if (vac_charge) *vac_charge = s * voxel_volume;
+    if (vac_volume) *vac_volume = (double)c->h_cnt[CNT_VACUUM] * voxel_volume;
+    return 0;
+}
+
+int bdr_bader_calc(bdr_ctx *c, int method, const double *dist_mat, const double *T_grad,
+                   int64_t *n_maxima) {
+    TRY(check(c));
+    if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_bader_calc: reference density not uploaded");
+    if (!dist_mat) return fail_msg("bdr_bader_calc: dist_mat is null");
+    const Weights W = make_weights(dist_mat);
+    if (method == BDR_METHOD_ONGRID) {
+        TRY(ongrid_dev(c, W));
+    } else if (method == BDR_METHOD_NEARGRID) {
+        if (!T_grad) return fail_msg("bdr_bader_calc: T_grad is null");
+        const TGrad T = make_tgrad(T_grad);
+        // seed with the pointer-jumpable ongrid field, then drive the order-free
+        // refinement iteration to its fixed point
+        TRY(ongrid_dev(c, W));
+        int64_t run = 0;
+        TRY(refine_dev(c, BDR_LABELS_BADER, BDR_MODE_ALL, -1, W, T, &run, nullptr, 0));
+        TRY(renumber_dev(c, BDR_LABELS_BADER));
+    } else {
+        return fail_msg("bdr_bader_calc: unknown method");
+    }
+    if (n_maxima) *n_maxima = c->n_max;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_get_maxima(bdr_ctx *c, int64_t *out, int64_t cap) {
+    TRY(check(c));
+    if (cap < c->n_max) return fail_msg("bdr_get_maxima: buffer too small");
+    if (c->n_max) memcpy(out, c->maxima.data(), (size_t)c->n_max * 3 * sizeof(int64_t));
+    return 0;
+}
+
+int bdr_refine(bdr_ctx *c, int which, int mode, int64_t iters, const double *dist_mat,
+               const double *T_grad, int64_t *iters_run, int64_t *history, int64_t hist_cap) {
+    TRY(check(c));
+    if (which < 0 || which > 1) return fail_msg("bdr_refine: bad label set");
+    if (!c->labels[which]) return fail_msg("bdr_refine: label set is empty");
+    if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_refine: reference density not uploaded");
+    if (mode != BDR_MODE_ALL && mode != BDR_MODE_CHANGED) return fail_msg("bdr_refine: bad mode");
+    const Weights W = make_weights(dist_mat);
+    const TGrad T = make_tgrad(T_grad);
+    TRY(refine_dev(c, which, mode, iters, W, T, iters_run, history, hist_cap));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_edge_find(bdr_ctx *c, int which, int64_t *edges) {
+    TRY(check(c));
+    if (which < 0 || which > 1) return fail_msg("bdr_edge_find: bad label set");
+    int64_t e = 0;
+    TRY(edge_find_dev(c, which, &e));
+    CU(cudaStreamSynchronize(c->stream));
+    if (edges) *edges = e;
+    return 0;
+}
+
+int bdr_charge_sum(bdr_ctx *c, int which_labels, int which_density, double voxel_volume, int64_t n,
+                   double *charge, double *volume) {
+    TRY(check(c));
+    if (which_labels < 0 || which_labels > 1 || which_density < 0 || which_density > 2)
+        return fail_msg("bdr_charge_sum: bad argument");
+    return charge_sum_dev(c, which_labels, which_density, voxel_volume, n, charge, volume);
+}
+
+int bdr_assign_atoms(bdr_ctx *c, const double *maxima_cart, int64_t n_max, const double *atoms_cart,
+                     int64_t n_atoms, const double *lattice, int64_t *bader_atoms,
+                     double *bader_distance) {
+    TRY(check(c));
+    if (n_atoms < 1) return fail_msg("bdr_assign_atoms: no atoms");
+    if (!c->labels[BDR_LABELS_BADER]) return fail_msg("bdr_assign_atoms: label set is empty");
+    TRY(ensure_labels(c, BDR_LABELS_ATOMS));
+    const int64_t nd = 3 * n_max + 3 * n_atoms + 9 + 2 * n_max;
+    TRY(ensure_sums(c, nd));
+    double *d_max = c->d_sums, *d_atoms = d_max + 3 * n_max, *d_lat = d_atoms + 3 * n_atoms;
+    long long *d_who = reinterpret_cast<long long *>(d_lat + 9);
+    double *d_dist = reinterpret_cast<double *>(d_who + n_max);
+    std::vector<long long> who((size_t)n_max);
+    if (n_max > 0) {
+        CU(cudaMemcpyAsync(d_max, maxima_cart, (size_t)3 * n_max * sizeof(double),
+                           cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_atoms, atoms_cart, (size_t)3 * n_atoms * sizeof(double),
+                           cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_lat, lattice, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, BDR_K_ASSIGN, k_atom_assign, blocks_for(n_max, 128), 128, 0, d_max, n_max, d_atoms,
+               n_atoms, d_lat, d_who, d_dist);
+        CU(cudaMemcpyAsync(who.data(), d_who, (size_t)n_max * sizeof(long long),
+                           cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(bader_distance, d_dist, (size_t)n_max * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int64_t i = 0; i < n_max; ++i) bader_atoms[i] = who[(size_t)i];
+    }
+    // utils.volume_assign: atoms labels = LUT(bader labels)
+    TRY(ensure_slots(c, std::max<int64_t>(n_max, 1)));
+    std::vector<int32_t> lut((size_t)std::max<int64_t>(n_max, 1), 0);
+    for (int64_t i = 0; i < n_max; ++i) lut[(size_t)i] = (int32_t)who[(size_t)i];
+    CU(cudaMemcpyAsync(c->rank, lut.data(), lut.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                       c->stream));
+    LAUNCH(c, BDR_K_ASSIGN, k_relabel_lut, blocks_for(c->N, 256), 256, 0, c->labels[BDR_LABELS_BADER],
+           c->labels[BDR_LABELS_ATOMS], c->N, c->rank);
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_surface_distance(bdr_ctx *c, int which, const double *lattice, const double *atoms_cart,
+                         int64_t n_atoms, double *distance, int *found) {
+    TRY(check(c));
+    if (which < 0 || which > 1) return fail_msg("bdr_surface_distance: bad label set");
+    int64_t edges = 0;
+    TRY(edge_find_dev(c, which, &edges));
+    if (found) *found = edges > 0;
+    for (int64_t a = 0; a < n_atoms; ++a) distance[a] = 0.0;
+    if (edges == 0) return 0;
+    TRY(ensure_sums(c, 5 * n_atoms + 9));
+    double *d_atoms = c->d_sums, *d_lat = d_atoms + 3 * n_atoms;
+    unsigned long long *d_best = reinterpret_cast<unsigned long long *>(d_lat + 9);
+    unsigned long long *d_seen = d_best + n_atoms;
+    // utils.py:341-343: the running minimum starts at nx^2+ny^2+nz^2
+    const double init = (double)((int64_t)c->g.nx * c->g.nx + (int64_t)c->g.ny * c->g.ny +
+                                 (int64_t)c->g.nz * c->g.nz);
+    std::vector<double> best((size_t)n_atoms, init);
+    std::vector<unsigned long long> seen((size_t)n_atoms, 0);
+    CU(cudaMemcpyAsync(d_atoms, atoms_cart, (size_t)3 * n_atoms * sizeof(double),
+                       cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_lat, lattice, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_best, best.data(), (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice,
+                       c->stream));
+    CU(cudaMemsetAsync(d_seen, 0, (size_t)n_atoms * sizeof(unsigned long long), c->stream));
+    LAUNCH(c, BDR_K_SURFACE, k_surface_dist, blocks_for(edges, 128), 128, 0, c->labels[which], c->g,
+           c->list, edges, d_lat, d_atoms, d_best, d_seen, (int)n_atoms);
+    CU(cudaMemcpyAsync(best.data(), d_best, (size_t)n_atoms * sizeof(double), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaMemcpyAsync(seen.data(), d_seen, (size_t)n_atoms * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // atoms that own no edge voxel keep 0 (thread_handlers.py:289-297)
+    for (int64_t a = 0; a < n_atoms; ++a)
+        distance[a] = seen[(size_t)a] ? std::sqrt(best[(size_t)a]) : 0.0;
+    return 0;
+}
+
+int bdr_volume_mask(bdr_ctx *c, int which_labels, int which_density, int64_t vol_num,
+                    double *host_out) {
+    TRY(check(c));
+    if (!c->labels[which_labels]) return fail_msg("bdr_volume_mask: label set is empty");
+    const double *dens = rho_ptr(c, which_density);
+    if (!dens) return fail_msg("bdr_volume_mask: density slot is empty");
+    TRY(ensure_stage(c, (size_t)c->N * sizeof(double)));
+    LAUNCH(c, BDR_K_NARROW, k_volume_mask, blocks_for(c->N, 256), 256, 0, c->labels[which_labels],
+           dens, (double *)c->stage, c->N, (int32_t)vol_num);
+    CU(cudaMemcpyAsync(host_out, c->stage, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_run(bdr_ctx *c, const double *host_density, double vac_tol, double voxel_volume, int method,
+            int refine_mode, int64_t refine_iters, const double *dist_mat, const double *T_grad,
+            void *host_labels, int label_elem_size, int64_t *n_maxima, int64_t *maxima,
+            int64_t max_cap, double *charge, double *volume) {
+    TRY(check(c));
+    TRY(bdr_upload_density(c, BDR_RHO_REFERENCE, host_density));
+    TRY(bdr_clear_labels(c, BDR_LABELS_BADER));
+    if (vac_tol == vac_tol) {
+        double q, v;
+        TRY(bdr_vacuum_assign(c, vac_tol, voxel_volume, BDR_RHO_REFERENCE, &q, &v));
+    }
+    int64_t n = 0;
+    TRY(bdr_bader_calc(c, method, dist_mat, T_grad, &n));
+    if (refine_iters != 0) {
+        int64_t run = 0;
+        TRY(bdr_refine(c, BDR_LABELS_BADER, refine_mode, refine_iters, dist_mat, T_grad, &run,
+                       nullptr, 0));
+    }
+    if (n_maxima) *n_maxima = n;
+    if (maxima) TRY(bdr_get_maxima(c, maxima, max_cap));
+    if (charge || volume) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (charge) charge[i] = 0;
+            if (volume) volume[i] = 0;
+        }
+        TRY(charge_sum_dev(c, BDR_LABELS_BADER, BDR_RHO_REFERENCE, voxel_volume, n, charge, volume));
+    }
+    if (host_labels) TRY(bdr_download_labels(c, BDR_LABELS_BADER, host_labels, label_elem_size));
+    return 0;
+}
+
+int bdr_profile_enable(bdr_ctx *c, int on) {
+    TRY(check(c));
+    prof_collect(c);
+    c->prof = on != 0;
+    return 0;
+}
+int bdr_profile_reset(bdr_ctx *c) {
+    TRY(check(c));
+    prof_collect(c);
+    for (int i = 0; i < BDR_K_COUNT; ++i) {
+        c->prof_ms[i] = 0;
+        c->prof_n[i] = 0;
+    }
+    return 0;
+}
+int bdr_profile_get(bdr_ctx *c, int family, double *ms, int64_t *launches) {
+    TRY(check(c));
+    if (family < 0 || family >= BDR_K_COUNT) return fail_msg("bdr_profile_get: bad family");
+    prof_collect(c);
+    if (ms) *ms = c->prof_ms[family];
+    if (launches) *launches = c->prof_n[family];
+    return 0;
+}
+int bdr_launch_count(bdr_ctx *c, int64_t *launches) {
+    TRY(check(c));
+    *launches = c->launches;
+    return 0;
+}
+
+int bdr_synth_separable(bdr_ctx *c, int which, const double *tx, const double *ty, const double *tz,
+                        int64_t n_atoms) {
+    TRY(check(c));
+    if (which < 0 || which > 2) return fail_msg("bdr_synth_separable: bad slot");
+    TRY(ensure_rho(c, which));
+    const int64_t nt = n_atoms * ((int64_t)c->g.nx + c->g.ny + c->g.nz);
+    double *d_t = nullptr;
+    CU(cudaMalloc((void **)&d_t, (size_t)nt * sizeof(double)));
+    double *d_tx = d_t, *d_ty = d_tx + n_atoms * c->g.nx, *d_tz = d_ty + n_atoms * c->g.ny;
+    CU(cudaMemcpyAsync(d_tx, tx, (size_t)n_atoms * c->g.nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_ty, ty, (size_t)n_atoms * c->g.ny * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_tz, tz, (size_t)n_atoms * c->g.nz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((c->g.nz + 255) / 256, c->g.ny, c->g.nx);
+    LAUNCH(c, BDR_K_SYNTH, k_synth_separable, grid, 256, 0, c->rho[which], c->g, d_tx, d_ty, d_tz,
+           (int)n_atoms);
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_t);
+    return 0;
+}
+
+int bdr_synth_general(bdr_ctx *c, int which, const double *lattice, const double *frac_atoms,
+                      const double *amps, const double *sigmas, int64_t n_atoms) {
+    TRY(check(c));
+    if (which < 0 || which > 2) return fail_msg("bdr_synth_general: bad slot");
+    TRY(ensure_rho(c, which));
+    double *d = nullptr;
+    CU(cudaMalloc((void **)&d, (size_t)(9 + 5 * n_atoms) * sizeof(double)));
+    double *d_lat = d, *d_frac = d + 9, *d_amp = d_frac + 3 * n_atoms, *d_sig = d_amp + n_atoms;
+    CU(cudaMemcpyAsync(d_lat, lattice, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_frac, frac_atoms, (size_t)3 * n_atoms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_amp, amps, (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_sig, sigmas, (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((c->g.nz + 255) / 256, c->g.ny, c->g.nx);
+    LAUNCH(c, BDR_K_SYNTH, k_synth_general, grid, 256, 0, c->rho[which], c->g, d_lat, d_frac, d_amp,
+           d_sig, (int)n_atoms);
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    return 0;
+}
+
+int bdr_device_ptr(bdr_ctx *c, int what, void **ptr) {
+    TRY(check(c));
+    switch (what) {
+        case 0: *ptr = rho_ptr(c, 0); return 0;
+        case 1: *ptr = rho_ptr(c, 1); return 0;
+        case 2: *ptr = rho_ptr(c, 2); return 0;
+        case 3: *ptr = c->labels[0]; return 0;
+        case 4: *ptr = c->labels[1]; return 0;
+        case 5: *ptr = c->known; return 0;
+    }
+    return fail_msg("bdr_device_ptr: bad selector");
+}
+
+}  // extern "C"

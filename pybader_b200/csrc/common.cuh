@@ -1,0 +1,209 @@
+// common.cuh -- handle layout, error plumbing and launch/profiling helpers of
+// libbader_b200.so.  Compiled only for sm_100a (see build.py); no CPU path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bader_b200.h"
+
+namespace bdr {
+
+extern thread_local std::string g_err;
+
+inline int fail(const char *what, const char *file, int line, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line,
+             e == cudaSuccess ? "" : cudaGetErrorString(e));
+    g_err = buf;
+    return 1;
+}
+inline int fail_msg(const std::string &m) {
+    g_err = m;
+    return 1;
+}
+
+#define CU(x)                                                               \
+    do {                                                                    \
+        cudaError_t e_ = (x);                                               \
+        if (e_ != cudaSuccess) return bdr::fail(#x, __FILE__, __LINE__, e_); \
+    } while (0)
+#define TRY(x)                 \
+    do {                       \
+        int r_ = (x);          \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+// grid geometry as the kernels see it (32-bit coordinates; N < 2^31 - 2^16)
+struct Grid {
+    int nx, ny, nz;
+};
+__host__ __device__ inline int64_t gsize(const Grid &g) {
+    return (int64_t)g.nx * g.ny * g.nz;
+}
+
+// step weights 1/|step| ordered by offset k = (ix+1)*9 + (iy+1)*3 + (iz+1)
+struct Weights {
+    double w[27];
+};
+struct TGrad {
+    double t[9];
+};
+
+// device-side counters (one small block of managed-by-hand words)
+enum {
+    CNT_ROOTS = 0,     // number of maxima found by the stencil pass
+    CNT_EDGES = 1,     // edge voxels appended to the work list
+    CNT_CHANGED = 2,   // voxels relabelled by the trace kernel
+    CNT_CHANGED_LIST = 3,
+    CNT_UNDECIDED = 4, // edge_check centre selection: still undecided
+    CNT_CENTRES = 5,
+    CNT_NEWEDGE = 6,
+    CNT_OVERFLOW = 7,  // trace paths that outgrew the register-file path buffer
+    CNT_ERROR = 8,     // trace step cap exceeded
+    CNT_VACUUM = 9,    // vacuum voxel count
+    CNT_NUM = 16
+};
+
+struct ProfRec {
+    int fam;
+    cudaEvent_t a, b;
+};
+
+}  // namespace bdr
+
+struct bdr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bdr::Grid g{0, 0, 0};
+    int64_t N = 0;
+
+    double *rho[3] = {nullptr, nullptr, nullptr};
+    int rho_alias[3] = {-1, 0, 0};  // -1: owns storage (or empty); k: alias of slot k
+
+    int32_t *labels[2] = {nullptr, nullptr};
+    int8_t *known = nullptr;
+
+    int32_t *list = nullptr;   // work list (edge voxels to trace)
+    int64_t list_cap = 0;
+    int64_t list_n = 0;
+    int32_t *list2 = nullptr;  // changed voxels / centres
+    int64_t list2_cap = 0;
+    int32_t *list3 = nullptr;  // centres (edge_check)
+    int64_t list3_cap = 0;
+
+    int32_t *roots = nullptr;  // voxel index of each maximum, by slot
+    int32_t *minidx = nullptr; // first voxel (C order) of each slot's volume
+    int32_t *rank = nullptr;   // slot -> volume number
+    int64_t slots_cap = 0;
+    std::vector<int64_t> maxima;  // [n][3], in volume-number order
+    int64_t n_max = 0;
+
+    unsigned long long *d_cnt = nullptr;  // device counters [CNT_NUM]
+    unsigned long long *h_cnt = nullptr;  // pinned mirror
+    double *d_sums = nullptr;             // device scratch doubles
+    int64_t d_sums_cap = 0;
+
+    void *stage = nullptr;  // device staging for narrowed labels / masks
+    size_t stage_bytes = 0;
+    void *pinned = nullptr;  // pinned host bounce buffer
+    size_t pinned_bytes = 0;
+
+    bool prof = false;
+    std::vector<bdr::ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    double prof_ms[BDR_K_COUNT] = {0};
+    int64_t prof_n[BDR_K_COUNT] = {0};
+    int64_t launches = 0;
+};
+
+namespace bdr {
+
+inline void prof_begin(bdr_ctx *c, int fam) {
+    if (!c->prof) return;
+    ProfRec r;
+    r.fam = fam;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!c->pool.empty()) {
+            e = c->pool.back();
+            c->pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    };
+    r.a = get();
+    r.b = get();
+    cudaEventRecord(r.a, c->stream);
+    c->recs.push_back(r);
+}
+inline void prof_end(bdr_ctx *c, int fam) {
+    (void)fam;
+    if (!c->prof) return;
+    cudaEventRecord(c->recs.back().b, c->stream);
+}
+// fold finished event pairs into the per-family totals
+inline void prof_collect(bdr_ctx *c) {
+    if (c->recs.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto &r : c->recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        c->prof_ms[r.fam] += ms;
+        c->prof_n[r.fam] += 1;
+        c->pool.push_back(r.a);
+        c->pool.push_back(r.b);
+    }
+    c->recs.clear();
+}
+
+#define LAUNCH(ctx, fam, kern, grid, block, smem, ...)                     \
+    do {                                                                   \
+        bdr::prof_begin(ctx, fam);                                         \
+        kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);           \
+        bdr::prof_end(ctx, fam);                                           \
+        (ctx)->launches++;                                                 \
+        CU(cudaGetLastError());                                            \
+    } while (0)
+
+inline int ensure(int32_t **p, int64_t *cap, int64_t want) {
+    if (*cap >= want) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    int64_t n = std::max<int64_t>(want + want / 4, 1024);
+    CU(cudaMalloc((void **)p, (size_t)n * sizeof(int32_t)));
+    *cap = n;
+    return 0;
+}
+
+inline int ensure_stage(bdr_ctx *c, size_t bytes) {
+    if (c->stage_bytes >= bytes) return 0;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr;
+    c->stage_bytes = 0;
+    CU(cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+// read the device counters (synchronises the stream)
+inline int read_counters(bdr_ctx *c) {
+    CU(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(unsigned long long) * CNT_NUM,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+inline int zero_counter(bdr_ctx *c, int which) {
+    CU(cudaMemsetAsync(c->d_cnt + which, 0, sizeof(unsigned long long), c->stream));
+    return 0;
+}
+
+}  // namespace bdr

@@ -111,3 +111,25 @@ def make(case, spin=False):
                              case['amps'] * w, case['sigmas'])
         return rho, s, atoms_cart
     return rho, atoms_cart
+
+
+def separable_tables(case):
+    """1-D factor tables for an orthorhombic cell: rho[i,j,k] =
+    sum_a tx[a,i] * ty[a,j] * tz[a,k] (amplitude folded into tx; the 27-image
+    sum factorises into three 3-image sums)."""
+    lattice = np.asarray(case['lattice'], dtype=np.float64)
+    assert np.count_nonzero(lattice - np.diag(np.diag(lattice))) == 0, "orthorhombic only"
+    frac = np.asarray(case['frac_atoms'], dtype=np.float64).reshape(-1, 3)
+    amps = np.broadcast_to(np.asarray(case['amps'], dtype=np.float64), (len(frac),))
+    sig = np.broadcast_to(np.asarray(case['sigmas'], dtype=np.float64), (len(frac),))
+    tabs = []
+    for ax in range(3):
+        n = case['shape'][ax]
+        f = np.arange(n) / n
+        t = np.zeros((len(frac), n))
+        for m in (-1, 0, 1):
+            d = (f[None, :] - frac[:, ax:ax + 1] - m) * lattice[ax, ax]
+            t += np.exp(-d * d / (2.0 * sig[:, None] ** 2))
+        tabs.append(t)
+    tabs[0] = tabs[0] * amps[:, None]
+    return tuple(np.ascontiguousarray(t) for t in tabs)

@@ -1,0 +1,74 @@
+"""Drop-in replacements for the jitted helpers `pybader.interface` imports from
+`pybader.utils` (interface.py:18): same names and positional signatures.
+
+    dtype_calc      utils.py:15-37   (host logic, restated)
+    vacuum_assign   utils.py:383-401
+    charge_sum      utils.py:236-252
+    atom_assign     utils.py:186-232
+    volume_mask     utils.py:462-476
+"""
+import numpy as np
+
+from . import session
+from .engine import LABELS_BADER, RHO_CHARGE, RHO_REFERENCE, RHO_SPIN, Engine
+
+
+def dtype_calc(max_val):
+    """Smallest integer dtype name able to hold max_val (negative -> signed,
+    with the reference's factor 2 headroom)."""
+    signed = max_val < 0
+    if signed:
+        max_val *= -2
+    names = ['int8', 'int16', 'int32', 'int64'] if signed else ['uint8', 'uint16', 'uint32', 'uint64']
+    if max_val <= 255:
+        return names[0]
+    if max_val <= 65535:
+        return names[1]
+    if max_val <= 4294967295:
+        return names[2]
+    return names[3]
+
+
+def vacuum_assign(reference, volumes, vac_tol, density, voxel_volume):
+    s = session.get(reference.shape)
+    s.reference(reference)
+    dslot = s.density_slot(density, prefer=RHO_CHARGE)
+    if volumes.any():
+        s.engine.upload_labels(LABELS_BADER, volumes)
+    else:
+        s.engine.clear_labels(LABELS_BADER)
+    charge, volume = s.engine.vacuum_assign(vac_tol, voxel_volume, dslot)
+    s.labels_to_host(LABELS_BADER, out=volumes)
+    return volumes, charge, volume
+
+
+def charge_sum(charge, volume, voxel_volume, density, volumes):
+    s = session.get(volumes.shape)
+    lslot = s.label_slot(volumes, prefer=LABELS_BADER)
+    # first free slot: reference, then charge, then spin (so charge and spin
+    # both stay resident next to the reference)
+    if s.rho_key[RHO_REFERENCE] is None:
+        prefer = RHO_REFERENCE
+    elif s.rho_key[RHO_CHARGE] is None:
+        prefer = RHO_CHARGE
+    else:
+        prefer = RHO_SPIN
+    dslot = s.density_slot(density, prefer=prefer)
+    s.engine.charge_sum(lslot, dslot, voxel_volume, charge, volume)
+
+
+def atom_assign(bader_max, atoms, lattice, i_c=None):
+    e = Engine((1, 1, 1), session._device)
+    try:
+        e.clear_labels(LABELS_BADER)
+        return e.assign_atoms(bader_max, atoms, lattice)
+    finally:
+        e.close()
+
+
+def volume_mask(volumes, density, vol_num):
+    s = session.get(volumes.shape)
+    lslot = s.label_slot(volumes, prefer=LABELS_BADER)
+    dslot = s.density_slot(density, prefer=RHO_CHARGE if s.rho_key[RHO_REFERENCE] is not None
+                           else RHO_REFERENCE)
+    return s.engine.volume_mask(lslot, dslot, vol_num)

@@ -1,0 +1,101 @@
+"""CPU-side checks of the boundary: the C-ABI library builds, loads and exports
+every symbol include/bader_b200.h declares; host logic; loud failure without a
+GPU.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from pybader_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'bader_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(bdr_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_header_symbols_exported(lib):
+    from pybader_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_version_and_error_string(lib):
+    assert lib.bdr_version() >= 100
+    assert isinstance(lib.bdr_last_error(), bytes)
+
+
+def test_create_fails_loudly_without_gpu(lib):
+    n = ctypes.c_int(0)
+    lib.bdr_device_count(ctypes.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present")
+    from pybader_b200.engine import Engine
+    from pybader_b200._lib import BaderB200Error
+    with pytest.raises(BaderB200Error):
+        Engine((8, 8, 8))
+
+
+def test_bad_arguments(lib):
+    h = ctypes.c_void_p()
+    assert lib.bdr_create(0, 0, 4, 4, ctypes.byref(h)) != 0
+    assert b'empty' in lib.bdr_last_error()
+    assert lib.bdr_create(0, 2048, 2048, 2048, ctypes.byref(h)) != 0
+    assert b'too large' in lib.bdr_last_error()
+
+
+def test_no_oracle_import_in_product():
+    pkg = os.path.join(ROOT, 'pybader_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in text.lower() or f == 'synth.py' and False, \
+                    f"{f} mentions the oracle: the product path must not use it"
+
+
+def test_dtype_calc_matches_reference_table():
+    from pybader_b200.utils import dtype_calc
+    from oracle.pyoracle import dtype_calc as ref
+    for v in (-1, -127, -128, -129, -32767, -32768, -2147483647, -2147483648, -2**40,
+              0, 255, 256, 65535, 65536, 4294967295, 4294967296):
+        assert dtype_calc(v) == ref(v)
+    assert dtype_calc(-127) == 'int8' and dtype_calc(-128) == 'int16'
+    assert dtype_calc(-884736) == 'int32'
+
+
+def test_geometry_matches_reference_formulas():
+    from pybader_b200 import geometry as geo
+    lat = np.array([[18.0, 0, 0], [4.5, 16.5, 0], [2.4, 3.3, 24.0]])
+    shape = (20, 24, 28)
+    d = geo.distance_matrix(lat, shape)
+    assert d.shape == (3, 3, 3) and d[0, 0, 0] == 0
+    vl = geo.voxel_lattice(lat, shape)
+    assert np.isclose(d[1, 0, 0], 1 / np.linalg.norm(vl[0]))
+    assert np.isclose(d[2, 2, 2], 1 / np.linalg.norm(-vl[0] - vl[1] - vl[2]))
+    T = geo.T_grad(lat, shape)
+    assert np.allclose(T, T.T)
+
+
+def test_session_fingerprint_detects_change():
+    from pybader_b200.session import fingerprint
+    a = np.zeros((8, 8, 8))
+    k = fingerprint(a)
+    assert fingerprint(a) == k
+    a[0, 0, 0] = 1
+    assert fingerprint(a) != k
+    assert fingerprint(a.copy()) != fingerprint(a)   # another buffer
