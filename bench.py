@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- neargrid + refine voxels/s on synthetic Gaussian-superposition
+densities (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one resident density:
+    labels := 0 ; bader_calc('neargrid') ; refine('neargrid', ('changed', 2))
+i.e. thread_handlers.bader_calc + thread_handlers.refine of the reference
+(thread_handlers.py:15-75, 128-236), the path BASELINE.json's metric names.
+
+`value`  = voxels / device time of the step, density already resident in HBM.
+`e2e`    = the same metric through the C ABI one-shot call `bdr_run` with HOST
+           buffers: pinned-host density in, narrowed labels + maxima out, the
+           H2D / D2H copies inside the timed region.
+`roofline` is for the dominant streaming kernel family of the step, from CUDA
+events recorded on the library's own stream around every launch.
+`cpu_baseline` times the CPU oracle (a single-threaded C port of the
+reference's numba kernels) on a bounded sample of the same workload family.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "neargrid+refine voxels/s"
+UNIT = "voxels/s"
+VOXEL = 22.5 / 1024.0      # Angstrom per voxel; BASELINE config 5 is 45 A over 2048
+SPACING = 204.8            # voxels between neighbouring atoms (1000 atoms in 2048^3)
+
+# weak scaling: 2^30 voxels per GPU; N=1 is the 1024^3 north-star target, N=8
+# is BASELINE config 5 (2048^3, 1000 atoms)
+SHAPES = {1: (1024, 1024, 1024), 2: (2048, 1024, 1024), 4: (2048, 2048, 1024),
+          8: (2048, 2048, 2048)}
+
+# algorithmic bytes per voxel of each streaming kernel family
+ALG_BYTES = {'stencil': 16, 'resolve': 8, 'relabel': 8, 'edge_flag': 5, 'edge_dilate': 2,
+             'first': 4, 'charge_sum': 12, 'vacuum': 12, 'narrow': 5}
+
+
+def workload_case(shape):
+    from pybader_b200 import synth
+    cells = tuple(max(1, int(round(s / SPACING))) for s in shape)
+    a = tuple(s * VOXEL for s in shape)
+    return synth.case_lattice_sites(shape, cells, a, seed=2048), cells
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------- CPU legs ----
+def cpu_sample_inputs(n):
+    """bounded sample of the workload family: n^3 periodic cell, same voxel size,
+    2^3 jittered atoms"""
+    from pybader_b200 import geometry as geo, synth
+    c = synth.case_lattice_sites((n, n, n), (2, 2, 2), (n * VOXEL,) * 3, seed=2048)
+    tx, ty, tz = synth.separable_tables(c)
+    rho = np.einsum('ai,aj,ak->ijk', tx, ty, tz, optimize=True)
+    rho = np.ascontiguousarray(rho)
+    return rho, geo.distance_matrix(c['lattice'], rho.shape), geo.T_grad(c['lattice'], rho.shape)
+
+
+def cpu_step(orc, rho, dist, T):
+    vol = np.zeros(rho.shape, dtype=np.int32)
+    _, vol = orc.bader_calc('neargrid', rho, vol, dist, T)
+    orc.refine('neargrid', ('changed', 2), rho, vol, dist, T)
+    return vol
+
+
+def cpu_baseline_leg(n=176):
+    from oracle import pyoracle as orc
+    rho, dist, T = cpu_sample_inputs(n)
+    cpu_step(orc, rho[:32, :32, :32].copy(), dist, T)          # load / warm the .so
+    t0 = time.perf_counter()
+    cpu_step(orc, rho, dist, T)
+    dt = time.perf_counter() - t0
+    return {"value": rho.size / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n}^3 periodic cell of the same workload family (voxel {VOXEL:.5f} A, "
+                      f"8 jittered atoms), oracle/bader_oracle.c neargrid + refine('changed',2), "
+                      f"{dt:.1f} s on one host core"}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (the C oracle port; the
+    reference itself is numba and cannot travel) on all host cores: one
+    independent brick per thread, like the reference's brick threading at its
+    ideal efficiency."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import pyoracle as orc
+    n = args.ref_sample
+    cores = os.cpu_count() or 1
+    rho, dist, T = cpu_sample_inputs(n)
+    bricks = [rho.copy() for _ in range(cores)]
+    cpu_step(orc, rho[:32, :32, :32].copy(), dist, T)
+
+    def one_step():
+        ths = [threading.Thread(target=cpu_step, args=(orc, b, dist, T)) for b in bricks]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    for _ in range(min(args.warmup, 1)):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = cores * rho.size / dt
+    shape = SHAPES.get(args.gpus, SHAPES[1])
+    sample = (f"{cores} independent {n}^3 bricks per step (one host thread each), same workload "
+              f"family; oracle C port of methods.neargrid + thread_handlers.refine('changed',2)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(shape), "method": "neargrid",
+                   "refine_method": "neargrid", "refine_mode": ["changed", 2]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(shape):
+    return (f"{shape[0]}x{shape[1]}x{shape[2]} periodic orthorhombic cell, jittered simple-lattice "
+            f"Gaussian superposition ({SPACING:.1f}-voxel atom spacing), neargrid + "
+            f"refine('changed',2)")
+
+
+# ---------------------------------------------------------------- GPU arm ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--size', type=int, default=0, help='override: cubic N^3 single-GPU grid')
+    ap.add_argument('--cpu-sample', type=int, default=176)
+    ap.add_argument('--ref-sample', type=int, default=112)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        return reference_arm(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
+    if world > 1:
+        from pybader_b200 import sharded
+        return sharded.bench(args, rank, world, local)
+
+    from pybader_b200 import build, geometry as geo, synth
+    build.build()
+    from pybader_b200.engine import Engine, LABELS_BADER
+
+    shape = (args.size,) * 3 if args.size else SHAPES[1]
+    N = int(np.prod(shape))
+    case, cells = workload_case(shape)
+    dist = geo.distance_matrix(case['lattice'], shape)
+    T = geo.T_grad(case['lattice'], shape)
+    dV = geo.voxel_volume(case['lattice'], shape)
+    e = Engine(shape, device=local)
+    e.synth_separable(0, *synth.separable_tables(case))
+    n_atoms = len(case['amps'])
+    mode = ('changed', 2)
+
+    def step():
+        e.clear_labels(LABELS_BADER)
+        mx = e.bader_calc('neargrid', dist, T)
+        hist = e.refine(LABELS_BADER, mode[0], mode[1], dist, T)
+        return mx, hist
+
+    for _ in range(args.warmup):
+        mx, hist = step()
+    n_max = mx.shape[0]
+
+    # ---- timed region: K steps, CUDA events on the library's stream ----------
+    clocks = ClockSampler(local)
+    clocks.start()
+    e.profile(True)
+    e.profile_reset()
+    l0 = e.launch_count()
+    e.synchronize()
+    e.timer_start()
+    for _ in range(args.steps):
+        step()
+    total_ms = e.timer_stop()
+    e.synchronize()
+    launches = e.launch_count() - l0
+    prof = e.profile_get()
+    tsteps, tvox = e.trace_steps()
+    e.profile(False)
+    clock_info = clocks.stop()
+    ms_per_step = total_ms / args.steps
+    value = N / (ms_per_step * 1e-3)
+
+    # ---- per-kernel accounting and the roofline object ---------------------
+    peak, peak_src = peaks()
+    kernels = {}
+    for name, (ms, n) in prof.items():
+        k = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps}
+        if name in ALG_BYTES:
+            gb = ALG_BYTES[name] * N * 1e-9
+            k["alg_bytes_per_voxel"] = ALG_BYTES[name]
+            k["achieved_gbs"] = gb / (ms / n * 1e-3)
+            k["frac"] = k["achieved_gbs"] / peak
+        kernels[name] = k
+    if 'trace' in kernels and tvox:
+        # gather-bound: 7 fp64 gathers + 1 known byte per trajectory step, label R+W per voxel
+        tb = tsteps * (7 * 8 + 1) + tvox * (4 + 4 + 4 + 1)
+        kernels['trace'].update({"alg_bytes_per_launch": tb / prof['trace'][1],
+                                 "achieved_gbs": tb * 1e-9 / (prof['trace'][0] * 1e-3),
+                                 "steps_per_voxel": tsteps / tvox,
+                                 "voxels_per_step": tvox / args.steps})
+        kernels['trace']["frac"] = kernels['trace']["achieved_gbs"] / peak
+    dom = max((k for k in kernels if 'achieved_gbs' in kernels[k]),
+              key=lambda k: kernels[k]['ms_per_step'])
+    dk = kernels[dom]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": dk['achieved_gbs'], "peak": peak,
+                "unit": "GB/s", "frac": dk['achieved_gbs'] / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": dk['ms_per_step'] / dk['launches_per_step'],
+                "share_of_step": dk['ms_per_step'] / ms_per_step}
+
+    # ---- e2e: host buffers through bdr_run -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import torch
+        from pybader_b200.utils import dtype_calc
+        ldt = np.dtype(dtype_calc(-n_max))
+        host_rho = torch.empty(N, dtype=torch.float64, pin_memory=True).numpy().reshape(shape)
+        host_lab = torch.empty(N * ldt.itemsize, dtype=torch.uint8,
+                               pin_memory=True).numpy().view(ldt).reshape(shape)
+        from pybader_b200._lib import check
+        check(e.lib.bdr_download_density(e.h, 0, host_rho.ctypes.data))
+        cap = max(1 << 12, 2 * n_max)
+        e.run(host_rho, None, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
+              want_sums=False, out_labels=host_lab)
+        e.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e.run(host_rho, None, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
+                  want_sums=False, out_labels=host_lab)
+        e.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": N / dt, "unit": UNIT, "h2d_bytes_per_step": N * 8,
+               "d2h_bytes_per_step": N * ldt.itemsize + n_max * 24, "ms_per_step": dt * 1e3,
+               "api": "bdr_run (C ABI, pinned host density in, narrowed labels + maxima out)"}
+        del host_rho, host_lab
+
+    cpu = None if args.no_cpu else cpu_baseline_leg(args.cpu_sample)
+    e.close()
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(shape), "atoms": n_atoms, "maxima": n_max,
+                   "method": "neargrid", "refine_method": "neargrid", "refine_mode": list(mode),
+                   "l2": "inputs (8 B/voxel density) are far larger than the 126 MB L2; no flush",
+                   "parallelism": "1 GPU"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clock_info, "kernels": kernels,
+        "refine_history_last_step": hist,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

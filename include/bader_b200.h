@@ -151,6 +151,13 @@ int bdr_profile_reset(bdr_ctx *ctx);
 int bdr_profile_get(bdr_ctx *ctx, int family, double *ms, int64_t *launches);
 /* number of kernels this library launched on the handle since creation      */
 int bdr_launch_count(bdr_ctx *ctx, int64_t *launches);
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of
+ * this library is launched on): start records an event, stop records a second
+ * one, synchronises and returns the elapsed milliseconds.                   */
+int bdr_timer_start(bdr_ctx *ctx);
+int bdr_timer_stop(bdr_ctx *ctx, double *ms);
+/* trajectory steps taken by the trace kernel since the last profile reset   */
+int bdr_trace_steps(bdr_ctx *ctx, int64_t *steps, int64_t *voxels);
 
 /* ---- synthetic inputs (bench / tests) ------------------------------------ */
 /* separable Gaussian superposition for orthorhombic cells: rho[i][j][k] =

@@ -45,6 +45,9 @@ SIGNATURES = {
     "bdr_profile_reset": ([_p], _int),
     "bdr_profile_get": ([_p, _int, ctypes.POINTER(_f64), ctypes.POINTER(_i64)], _int),
     "bdr_launch_count": ([_p, ctypes.POINTER(_i64)], _int),
+    "bdr_timer_start": ([_p], _int),
+    "bdr_timer_stop": ([_p, ctypes.POINTER(_f64)], _int),
+    "bdr_trace_steps": ([_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
     "bdr_synth_separable": ([_p, _int, _p, _p, _p, _i64], _int),
     "bdr_synth_general": ([_p, _int, _p, _p, _p, _p, _i64], _int),
     "bdr_device_ptr": ([_p, _int, _pp], _int),

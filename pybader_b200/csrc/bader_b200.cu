@@ -214,6 +214,7 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
     const int step_cap = 1 << 20;
     CU(cudaMemsetAsync(c->d_cnt + CNT_CHANGED, 0, sizeof(unsigned long long) * 2, c->stream));
     CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
+    TRY(zero_counter(c, CNT_STEPS));
     LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n, 128), 128, 0,
            rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, W, T, c->list, n,
            (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
@@ -240,6 +241,8 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
         if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
     }
     *changed = (int64_t)c->h_cnt[CNT_CHANGED];
+    c->trace_steps += (int64_t)c->h_cnt[CNT_STEPS];
+    c->trace_voxels += n;
     return 0;
 }
 
@@ -443,6 +446,8 @@ int bdr_destroy(bdr_ctx *c) {
         cudaEventDestroy(r.b);
     }
     for (auto e : c->pool) cudaEventDestroy(e);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -758,6 +763,8 @@ int bdr_profile_reset(bdr_ctx *c) {
         c->prof_ms[i] = 0;
         c->prof_n[i] = 0;
     }
+    c->trace_steps = 0;
+    c->trace_voxels = 0;
     return 0;
 }
 int bdr_profile_get(bdr_ctx *c, int family, double *ms, int64_t *launches) {
@@ -771,6 +778,31 @@ int bdr_profile_get(bdr_ctx *c, int family, double *ms, int64_t *launches) {
 int bdr_launch_count(bdr_ctx *c, int64_t *launches) {
     TRY(check(c));
     *launches = c->launches;
+    return 0;
+}
+int bdr_timer_start(bdr_ctx *c) {
+    TRY(check(c));
+    if (!c->t0) {
+        CU(cudaEventCreate(&c->t0));
+        CU(cudaEventCreate(&c->t1));
+    }
+    CU(cudaEventRecord(c->t0, c->stream));
+    return 0;
+}
+int bdr_timer_stop(bdr_ctx *c, double *ms) {
+    TRY(check(c));
+    if (!c->t0) return fail_msg("bdr_timer_stop: timer was not started");
+    CU(cudaEventRecord(c->t1, c->stream));
+    CU(cudaEventSynchronize(c->t1));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, c->t0, c->t1));
+    *ms = f;
+    return 0;
+}
+int bdr_trace_steps(bdr_ctx *c, int64_t *steps, int64_t *voxels) {
+    TRY(check(c));
+    if (steps) *steps = c->trace_steps;
+    if (voxels) *voxels = c->trace_voxels;
     return 0;
 }
 

@@ -68,6 +68,7 @@ enum {
     CNT_OVERFLOW = 7,  // trace paths that outgrew the register-file path buffer
     CNT_ERROR = 8,     // trace step cap exceeded
     CNT_VACUUM = 9,    // vacuum voxel count
+    CNT_STEPS = 10,    // trajectory steps taken by the trace kernel (accounting)
     CNT_NUM = 16
 };
 
@@ -121,6 +122,8 @@ struct bdr_ctx {
     double prof_ms[BDR_K_COUNT] = {0};
     int64_t prof_n[BDR_K_COUNT] = {0};
     int64_t launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int64_t trace_steps = 0, trace_voxels = 0;
 };
 
 namespace bdr {

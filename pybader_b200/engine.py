@@ -193,6 +193,19 @@ class Engine:
         check(self.lib.bdr_launch_count(self.h, ctypes.byref(n)))
         return n.value
 
+    def timer_start(self):
+        check(self.lib.bdr_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double(0)
+        check(self.lib.bdr_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def trace_steps(self):
+        s, v = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self.lib.bdr_trace_steps(self.h, ctypes.byref(s), ctypes.byref(v)))
+        return s.value, v.value
+
     def synchronize(self):
         check(self.lib.bdr_synchronize(self.h))
 

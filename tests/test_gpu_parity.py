@@ -256,27 +256,41 @@ def test_ongrid_refine_vs_oracle_bit_exact(th, orc, seeded, mode):
     assert [c for _, c in th.refine.last_history][:len(log)] == [c for _, c in log]
 
 
-def test_neargrid_vs_oracle(th, ut, orc, seeded):
+@pytest.mark.parametrize('mode', [('changed', 2), ('all', 2)])
+def test_neargrid_vs_oracle(th, ut, orc, seeded, mode):
     s = seeded
     mx, vol = th.bader_calc('neargrid', s['rho'], gpu_fresh(ut, s), s['dist_mat'], s['T_grad'], 1)
-    th.refine('neargrid', ('changed', 2), s['rho'], vol, s['dist_mat'], s['T_grad'], 1)
+    th.refine('neargrid', mode, s['rho'], vol, s['dist_mat'], s['T_grad'], 1)
     rmx, rvol = orc.bader_calc('neargrid', s['rho'], oracle_fresh(orc, s), s['dist_mat'], s['T_grad'])
-    orc.refine('neargrid', ('changed', 2), s['rho'], rvol, s['dist_mat'], s['T_grad'])
+    orc.refine('neargrid', mode, s['rho'], rvol, s['dist_mat'], s['T_grad'])
     key = lambda m: sorted(map(tuple, m.tolist()))
     assert key(mx) == key(rmx)
-    ndiff = check_neargrid(vol, mx, rvol, rmx, s['rho'], orc, s['name'])
-    n = mx.shape[0]
-    q, v, rq, rv = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
-    ut.charge_sum(q, v, s['voxel_volume'], s['rho'], vol)
-    orc.charge_sum(rq, rv, s['voxel_volume'], s['rho'], rvol)
     order = {tuple(m): i for i, m in enumerate(rmx.tolist())}
     perm = np.array([order[tuple(m)] for m in mx.tolist()])
+    n = mx.shape[0]
+    # The reference's 'changed' mode relabels a few VACUUM voxels next to edges
+    # that moved in its first iteration (edge_check does not test for vacuum,
+    # refinement.py:446-448).  Which ones depends on its
+    # scan-order dependent raw labels, so they cannot be reproduced; they are
+    # counted and credited explicitly instead of hiding them in the tolerance.
+    quirk = (vol == -1) & (rvol >= 0)
+    if mode[0] == 'all' or s['vacuum_tol'] is None:
+        assert not quirk.any()
+    assert quirk.sum() <= max(3, 1e-4 * vol.size)
+    vol_cmp = vol.copy()
+    inv = np.argsort(perm)
+    vol_cmp[quirk] = inv[rvol[quirk]]
+    ndiff = check_neargrid(vol_cmp, mx, rvol, rmx, s['rho'], orc, s['name'])
+    q, v, rq, rv = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    ut.charge_sum(q, v, s['voxel_volume'], s['rho'], vol_cmp)
+    orc.charge_sum(rq, rv, s['voxel_volume'], s['rho'], rvol)
     np.testing.assert_allclose(q, rq[perm], rtol=REL_TOL, atol=1e-9)
     np.testing.assert_allclose(v, rv[perm], rtol=REL_TOL)
     # numbering: volume numbers ascend with each volume's first voxel
     first = [int(np.flatnonzero(vol.ravel() == k)[0]) for k in range(n)]
     assert first == sorted(first)
-    print(f"{s['name']}: {ndiff} of {vol.size} voxels differ from the reference path")
+    print(f"{s['name']} {mode}: {ndiff} of {vol.size} voxels differ from the reference path, "
+          f"{int(quirk.sum())} vacuum voxels relabelled by the reference only")
 
 
 # ------------------------------------------------ properties at size -------
