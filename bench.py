@@ -42,7 +42,7 @@ SHAPES = {1: (1024, 1024, 1024), 2: (2048, 1024, 1024), 4: (2048, 2048, 1024),
           8: (2048, 2048, 2048)}
 
 # algorithmic bytes per voxel of each streaming kernel family
-ALG_BYTES = {'stencil': 16, 'resolve': 8, 'relabel': 8, 'edge_flag': 5, 'edge_dilate': 2,
+ALG_BYTES = {'stencil': 12, 'resolve': 8, 'relabel': 8, 'edge_flag': 5, 'edge_dilate': 2,
              'first': 4, 'charge_sum': 12, 'vacuum': 12, 'narrow': 5}
 
 

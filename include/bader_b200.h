@@ -50,7 +50,8 @@ enum {
     BDR_K_NARROW = 11,     /* int32 -> int8/16/64 staging for D2H     */
     BDR_K_SYNTH = 12,      /* synthetic density generator             */
     BDR_K_FIRST = 13,      /* first-voxel (numbering) pass            */
-    BDR_K_COUNT = 14
+    BDR_K_EDGE_CONFIRM = 14, /* edge candidates -> edges (density test) */
+    BDR_K_COUNT = 15
 };
 
 const char *bdr_last_error(void);
@@ -169,6 +170,15 @@ int bdr_synth_separable(bdr_ctx *ctx, int which, const double *tx, const double 
 int bdr_synth_general(bdr_ctx *ctx, int which, const double *lattice,
                       const double *frac_atoms, const double *amps,
                       const double *sigmas, int64_t n_atoms);
+
+/* ---- options ------------------------------------------------------------- */
+/* BDR_OPT_VERIFY_FIXED_POINT (default 0): bader_calc('neargrid') drives the
+ * labels to quiescence with one full edge pass plus incremental rounds; with
+ * 1 it additionally repeats full passes until one changes nothing, so the
+ * labels are certified to be a fixed point of the reference's refinement
+ * iteration before any refine() call.                                       */
+enum { BDR_OPT_VERIFY_FIXED_POINT = 0 };
+int bdr_set_option(bdr_ctx *ctx, int option, int64_t value);
 
 /* device pointers, for torch.distributed halo plumbing in the sharded path  */
 int bdr_device_ptr(bdr_ctx *ctx, int what, void **ptr);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "bdr_trace_steps": ([_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
     "bdr_synth_separable": ([_p, _int, _p, _p, _p, _i64], _int),
     "bdr_synth_general": ([_p, _int, _p, _p, _p, _p, _i64], _int),
+    "bdr_set_option": ([_p, _int, _i64], _int),
     "bdr_device_ptr": ([_p, _int, _pp], _int),
 }
 

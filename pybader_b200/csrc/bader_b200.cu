@@ -2,13 +2,20 @@
 // include/bader_b200.h on top of the kernels in kernels.cuh.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace bdr {
 thread_local std::string g_err;
 
-constexpr int TX = 8, TY = 8, TZ = 32;  // stencil tile (z fastest)
+constexpr int TX = 8, TY = 8, TZ = 32;   // edge-pass tile (z fastest)
+constexpr int SX = 16;                   // stencil tile depth along x (the marched axis)
 
-static dim3 tile_grid(const Grid &g) {
-    return dim3((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + TX - 1) / TX);
+static dim3 tile_grid(const Grid &g, int tx = TX) {
+    return dim3((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + tx - 1) / tx);
+}
+constexpr size_t stencil_smem() {
+    return (size_t)(SX + 2) * (TY + 2) * (TZ + 2) * sizeof(double) +
+           (size_t)SX * TY * TZ * sizeof(int32_t);
 }
 static unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -44,6 +51,7 @@ static int ensure_labels(bdr_ctx *c, int which) {
     if (c->labels[which]) return 0;
     CU(cudaMalloc((void **)&c->labels[which], (size_t)c->N * sizeof(int32_t)));
     CU(cudaMemsetAsync(c->labels[which], 0, (size_t)c->N * sizeof(int32_t), c->stream));
+    if (which == BDR_LABELS_BADER) c->vac_mode = 0;
     return 0;
 }
 static int ensure_known(bdr_ctx *c) {
@@ -116,14 +124,25 @@ static int rank_from_first(bdr_ctx *c, int64_t n, std::vector<int32_t> &order, b
 static int ongrid_dev(bdr_ctx *c, const Weights &W) {
     TRY(ensure_labels(c, BDR_LABELS_BADER));
     TRY(ensure_slots(c, 4096));
-    const size_t smem = (size_t)(TX + 2) * (TY + 2) * (TZ + 2) * sizeof(double) +
-                       (size_t)TX * TY * TZ * sizeof(int32_t);
+    const size_t smem = stencil_smem();
     int32_t *code = c->labels[BDR_LABELS_BADER];
+    const double *rho = rho_ptr(c, BDR_RHO_REFERENCE);
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_ROOTS));
-        LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<TX, TY, TZ>), tile_grid(c->g), 256, smem,
-               rho_ptr(c, BDR_RHO_REFERENCE), code, c->g, W, c->d_cnt + CNT_ROOTS, c->roots,
-               c->slots_cap);
+        // vacuum comes from the fused tolerance test when the labels were made
+        // by bdr_vacuum_assign / bdr_clear_labels on this handle, else from
+        // the label array itself (-1 entries)
+        if (c->vac_mode == VAC_NONE)
+            LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_NONE>), tile_grid(c->g, SX),
+                   256, smem, rho, code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap);
+        else if (c->vac_mode == VAC_TOL)
+            LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_TOL>), tile_grid(c->g, SX),
+                   256, smem, rho, code, c->g, W, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots,
+                   c->slots_cap);
+        else
+            LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>),
+                   tile_grid(c->g, SX), 256, smem, rho, code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS,
+                   c->roots, c->slots_cap);
         TRY(read_counters(c));
         const int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
         if (n <= c->slots_cap) break;
@@ -151,7 +170,7 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W) {
         c->maxima[(size_t)r * 3 + 1] = (v / c->g.nz) % c->g.ny;
         c->maxima[(size_t)r * 3 + 2] = v % c->g.nz;
     }
-    LAUNCH(c, BDR_K_RELABEL, k_relabel_slots, blocks_for(c->N, 256), 256, 0, code, c->N, c->rank);
+    LAUNCH(c, BDR_K_RELABEL, k_relabel_slots, blocks_for(c->N, 1024), 256, 0, code, c->N, c->rank);
     return 0;
 }
 
@@ -160,7 +179,7 @@ static int renumber_dev(bdr_ctx *c, int which) {
     const int64_t n = c->n_max;
     if (n == 0) return 0;
     CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
-    LAUNCH(c, BDR_K_FIRST, k_first_voxel, blocks_for(c->N, 256), 256, 0, c->labels[which], c->N,
+    LAUNCH(c, BDR_K_FIRST, k_first_voxel, blocks_for(c->N, 1024), 256, 0, c->labels[which], c->N,
            c->minidx);
     std::vector<int32_t> order;
     bool ident = true;
@@ -171,7 +190,7 @@ static int renumber_dev(bdr_ctx *c, int which) {
         for (int k = 0; k < 3; ++k)
             mx[(size_t)r * 3 + k] = c->maxima[(size_t)order[(size_t)r] * 3 + k];
     c->maxima.swap(mx);
-    LAUNCH(c, BDR_K_RELABEL, k_relabel_lut, blocks_for(c->N, 256), 256, 0, c->labels[which],
+    LAUNCH(c, BDR_K_RELABEL, k_relabel_lut, blocks_for(c->N, 1024), 256, 0, c->labels[which],
            c->labels[which], c->N, c->rank);
     return 0;
 }
@@ -182,24 +201,55 @@ static int renumber_dev(bdr_ctx *c, int which) {
 static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges) {
     TRY(ensure_known(c));
     if (!c->labels[which]) return fail_msg("edge_find: label set is empty");
-    TRY(ensure(&c->list, &c->list_cap, std::max<int64_t>(c->N / 8, 1024)));
+    TRY(ensure(&c->list, &c->list_cap, std::max<int64_t>(c->N / 16, 1024)));
     TRY(zero_counter(c, CNT_EDGES));
-    LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_flags<TX, TY, TZ>), tile_grid(c->g), 256, 0,
-           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->d_cnt + CNT_EDGES,
-           c->list, c->list_cap);
+    LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_candidates<TX, TY, TZ>), tile_grid(c->g), 256, 0,
+           c->labels[which], c->known, c->g, c->d_cnt + CNT_EDGES, c->list, c->list_cap);
     TRY(read_counters(c));
-    const int64_t n = (int64_t)c->h_cnt[CNT_EDGES];
+    int64_t n = (int64_t)c->h_cnt[CNT_EDGES];
     if (n > c->list_cap) {
         TRY(ensure(&c->list, &c->list_cap, n));
         TRY(zero_counter(c, CNT_EDGES));
         LAUNCH(c, BDR_K_EDGE_FLAG, k_compact_known, blocks_for(c->N, 256), 256, 0, c->known, c->N,
                (int8_t)-2, c->d_cnt + CNT_EDGES, c->list, c->list_cap);
     }
-    if (n > 0)
+    c->list_n = n;  // includes tomb-stoned maxima; the trace kernel skips them
+    int64_t confirmed = 0;
+    if (n > 0) {
+        TRY(zero_counter(c, CNT_NEWEDGE));
+        LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_confirm, blocks_for(n, 128), 128, 0,
+               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->list, n,
+               c->d_cnt + CNT_NEWEDGE);
         LAUNCH(c, BDR_K_EDGE_DILATE, (k_edge_dilate<TX, TY, TZ>), tile_grid(c->g), 256, 0, c->known,
                c->g);
-    c->list_n = n;
-    *edges = n;
+        TRY(read_counters(c));
+        confirmed = (int64_t)c->h_cnt[CNT_NEWEDGE];
+    }
+    *edges = confirmed;
+    return 0;
+}
+
+// incremental edge update between full passes (kernels.cuh K5'): consumes the
+// changed list (c->list2), produces the next trace list (c->list)
+static int incremental_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *queued) {
+    *queued = 0;
+    c->list_n = 0;
+    if (n_changed == 0) return 0;
+    TRY(ensure(&c->list, &c->list_cap, std::min<int64_t>(n_changed * 27, c->N)));
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_mark, blocks_for(n_changed, 128), 128, 0, c->known, c->list2,
+           n_changed);
+    TRY(zero_counter(c, CNT_NEWEDGE));
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_classify, blocks_for(n_changed * 27, 128), 128, 0,
+           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->list2, n_changed,
+           c->d_cnt + CNT_NEWEDGE, c->list, c->list_cap);
+    TRY(read_counters(c));
+    const int64_t nq = (int64_t)c->h_cnt[CNT_NEWEDGE];
+    if (nq > c->list_cap) return fail_msg("incremental queue overflow");
+    if (nq > 0)
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_dilate, blocks_for(nq * 27, 128), 128, 0, c->known, c->g,
+               c->list, nq);
+    c->list_n = nq;
+    *queued = nq;
     return 0;
 }
 
@@ -327,6 +377,34 @@ static int refine_dev(bdr_ctx *c, int which, int mode, int64_t iters, const Weig
     return 0;
 }
 
+// bader_calc('neargrid'): drive labels to the fixed point of the reference's
+// order-free refinement iteration ("every edge voxel carries the label its own
+// trajectory ends in").  One full edge pass + trace, then cheap incremental
+// rounds around the voxels that changed, then a full pass to confirm; repeat
+// until a full pass changes nothing.
+static int converge_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T) {
+    const bool dbg = getenv("BDR_DEBUG") != nullptr;
+    const int max_outer = c->verify_fixed_point ? 64 : 1;
+    for (int outer = 0; outer < max_outer; ++outer) {
+        int64_t edges = 0, changed = 0;
+        TRY(edge_find_dev(c, which, &edges));
+        if (edges == 0) return 0;
+        TRY(trace_dev(c, which, W, T, &changed, true));
+        if (dbg) fprintf(stderr, "[bdr] full pass %d: edges %lld changed %lld\n", outer,
+                         (long long)edges, (long long)changed);
+        if (changed == 0) return 0;
+        for (int inner = 0; inner < 4096 && changed > 0; ++inner) {
+            int64_t queued = 0;
+            TRY(incremental_dev(c, which, changed, &queued));
+            TRY(trace_dev(c, which, W, T, &changed, true));
+            if (dbg) fprintf(stderr, "[bdr]   incremental %d: queued %lld changed %lld\n", inner,
+                             (long long)queued, (long long)changed);
+        }
+    }
+    if (!c->verify_fixed_point) return 0;
+    return fail_msg("bader_calc(neargrid): refinement did not reach a fixed point");
+}
+
 template <typename T>
 static int download_cast(bdr_ctx *c, const int32_t *src, void *host) {
     TRY(ensure_stage(c, (size_t)c->N * sizeof(T)));
@@ -419,10 +497,12 @@ int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out) {
     CU(cudaMalloc((void **)&c->d_cnt, sizeof(unsigned long long) * CNT_NUM));
     CU(cudaMemsetAsync(c->d_cnt, 0, sizeof(unsigned long long) * CNT_NUM, c->stream));
     CU(cudaMallocHost((void **)&c->h_cnt, sizeof(unsigned long long) * CNT_NUM));
-    const size_t smem = (size_t)(TX + 2) * (TY + 2) * (TZ + 2) * sizeof(double) +
-                       (size_t)TX * TY * TZ * sizeof(int32_t);
-    CU(cudaFuncSetAttribute(k_ongrid_pointers<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)smem));
+    CU(cudaFuncSetAttribute(k_ongrid_pointers<SX, TY, TZ, VAC_NONE>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
+    CU(cudaFuncSetAttribute(k_ongrid_pointers<SX, TY, TZ, VAC_TOL>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
+    CU(cudaFuncSetAttribute(k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
     *out = c;
     return 0;
 }
@@ -497,6 +577,7 @@ int bdr_clear_labels(bdr_ctx *c, int which) {
     if (which < 0 || which > 1) return fail_msg("bdr_clear_labels: bad argument");
     TRY(ensure_labels(c, which));
     CU(cudaMemsetAsync(c->labels[which], 0, (size_t)c->N * sizeof(int32_t), c->stream));
+    if (which == BDR_LABELS_BADER) c->vac_mode = VAC_NONE;
     return 0;
 }
 
@@ -504,6 +585,7 @@ int bdr_upload_labels(bdr_ctx *c, int which, const void *host, int elem_size) {
     TRY(check(c));
     if (which < 0 || which > 1 || !host) return fail_msg("bdr_upload_labels: bad argument");
     TRY(ensure_labels(c, which));
+    if (which == BDR_LABELS_BADER) c->vac_mode = VAC_LABELS;
     switch (elem_size) {
         case 1: return upload_cast<int8_t>(c, c->labels[which], host);
         case 2: return upload_cast<int16_t>(c, c->labels[which], host);
@@ -558,6 +640,10 @@ int bdr_vacuum_assign(bdr_ctx *c, double vac_tol, double voxel_volume, int which
     double s = 0;
     CU(cudaMemcpyAsync(&s, c->d_sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     TRY(read_counters(c));
+    // the stencil pass may re-derive the mask from the tolerance only if the
+    // labels held nothing but zeros before this call
+    c->vac_mode = (c->vac_mode == VAC_NONE) ? VAC_TOL : VAC_LABELS;
+    c->vac_tol = vac_tol;
     if (vac_charge) *vac_charge = s * voxel_volume;
     if (vac_volume) *vac_volume = (double)c->h_cnt[CNT_VACUUM] * voxel_volume;
     return 0;
@@ -577,12 +663,12 @@ int bdr_bader_calc(bdr_ctx *c, int method, const double *dist_mat, const double 
         // seed with the pointer-jumpable ongrid field, then drive the order-free
         // refinement iteration to its fixed point
         TRY(ongrid_dev(c, W));
-        int64_t run = 0;
-        TRY(refine_dev(c, BDR_LABELS_BADER, BDR_MODE_ALL, -1, W, T, &run, nullptr, 0));
+        TRY(converge_dev(c, BDR_LABELS_BADER, W, T));
         TRY(renumber_dev(c, BDR_LABELS_BADER));
     } else {
         return fail_msg("bdr_bader_calc: unknown method");
     }
+    c->vac_mode = VAC_LABELS;
     if (n_maxima) *n_maxima = c->n_max;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -661,7 +747,7 @@ int bdr_assign_atoms(bdr_ctx *c, const double *maxima_cart, int64_t n_max, const
     for (int64_t i = 0; i < n_max; ++i) lut[(size_t)i] = (int32_t)who[(size_t)i];
     CU(cudaMemcpyAsync(c->rank, lut.data(), lut.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
                        c->stream));
-    LAUNCH(c, BDR_K_ASSIGN, k_relabel_lut, blocks_for(c->N, 256), 256, 0, c->labels[BDR_LABELS_BADER],
+    LAUNCH(c, BDR_K_ASSIGN, k_relabel_lut, blocks_for(c->N, 1024), 256, 0, c->labels[BDR_LABELS_BADER],
            c->labels[BDR_LABELS_ATOMS], c->N, c->rank);
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -844,6 +930,14 @@ int bdr_synth_general(bdr_ctx *c, int which, const double *lattice, const double
     CU(cudaStreamSynchronize(c->stream));
     cudaFree(d);
     return 0;
+}
+
+int bdr_set_option(bdr_ctx *c, int option, int64_t value) {
+    TRY(check(c));
+    switch (option) {
+        case BDR_OPT_VERIFY_FIXED_POINT: c->verify_fixed_point = value != 0; return 0;
+    }
+    return fail_msg("bdr_set_option: unknown option");
 }
 
 int bdr_device_ptr(bdr_ctx *c, int what, void **ptr) {

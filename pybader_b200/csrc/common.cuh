@@ -89,6 +89,9 @@ struct bdr_ctx {
     int rho_alias[3] = {-1, 0, 0};  // -1: owns storage (or empty); k: alias of slot k
 
     int32_t *labels[2] = {nullptr, nullptr};
+    int vac_mode = 0;      // how the stencil pass learns the vacuum mask (VAC_* in kernels.cuh)
+    double vac_tol = 0.0;
+    bool verify_fixed_point = false;  // BDR_OPT_VERIFY_FIXED_POINT
     int8_t *known = nullptr;
 
     int32_t *list = nullptr;   // work list (edge voxels to trace)

@@ -17,7 +17,8 @@ REFINE_METHODS = {'neargrid': 1}                # refinement.__contains__, refin
 MODES = {'all': 0, 'changed': 1}
 
 FAMILIES = ['vacuum', 'stencil', 'resolve', 'relabel', 'edge_flag', 'edge_dilate', 'trace',
-            'edge_check', 'charge_sum', 'assign', 'surface', 'narrow', 'synth', 'first']
+            'edge_check', 'charge_sum', 'assign', 'surface', 'narrow', 'synth', 'first',
+            'edge_confirm']
 
 
 def _f64(a):
@@ -218,6 +219,9 @@ class Engine:
     def synth_general(self, which, lattice, frac_atoms, amps, sigmas):
         l, f, a, s = _f64(lattice), _f64(frac_atoms), _f64(amps), _f64(sigmas)
         check(self.lib.bdr_synth_general(self.h, which, _ptr(l), _ptr(f), _ptr(a), _ptr(s), f.shape[0]))
+
+    def set_option(self, option, value):
+        check(self.lib.bdr_set_option(self.h, int(option), int(value)))
 
     def device_ptr(self, what):
         p = ctypes.c_void_p()
