@@ -8,7 +8,7 @@ namespace bdr {
 thread_local std::string g_err;
 
 constexpr int TX = 8, TY = 8, TZ = 32;   // edge-pass tile (z fastest)
-constexpr int SX = 16;                   // stencil tile depth along x (the marched axis)
+constexpr int SX = 15;                   // stencil tile depth along x (the marched axis)
 
 static dim3 tile_grid(const Grid &g, int tx = TX) {
     return dim3((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + tx - 1) / tx);
@@ -27,6 +27,17 @@ static Weights make_weights(const double *dist_mat) {
                 W.w[(ix + 1) * 9 + (iy + 1) * 3 + (iz + 1)] =
                     dist_mat[((ix + 3) % 3) * 9 + ((iy + 3) % 3) * 3 + ((iz + 3) % 3)];
     return W;
+}
+// the stencil kernel keeps 13 weights: w(-d) must equal w(d) bit for bit
+static bool weights_symmetric(const Weights &W) {
+    for (int k = 0; k < 13; ++k)
+        if (memcmp(&W.w[k], &W.w[26 - k], sizeof(double)) != 0) return false;
+    return true;
+}
+static HalfWeights half_weights(const Weights &W) {
+    HalfWeights h;
+    for (int k = 0; k < 14; ++k) h.w[k] = W.w[k];
+    return h;
 }
 static TGrad make_tgrad(const double *T) {
     TGrad t;
@@ -57,6 +68,15 @@ static int ensure_labels(bdr_ctx *c, int which) {
 static int ensure_known(bdr_ctx *c) {
     if (c->known) return 0;
     CU(cudaMalloc((void **)&c->known, (size_t)c->N));
+    return 0;
+}
+static int ensure_tile_flags(bdr_ctx *c, size_t n) {
+    if (c->tile_flag_n >= n) return 0;
+    if (c->tile_flag) cudaFree(c->tile_flag);
+    c->tile_flag = nullptr;
+    c->tile_flag_n = 0;
+    CU(cudaMalloc((void **)&c->tile_flag, n));
+    c->tile_flag_n = n;
     return 0;
 }
 static int ensure_rho(bdr_ctx *c, int which) {
@@ -121,12 +141,15 @@ static int rank_from_first(bdr_ctx *c, int64_t n, std::vector<int32_t> &order, b
 // ---------------------------------------------------------------------------
 // ongrid: stencil -> pointer codes -> resolve -> numbering
 // ---------------------------------------------------------------------------
-static int ongrid_dev(bdr_ctx *c, const Weights &W) {
+static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
     TRY(ensure_labels(c, BDR_LABELS_BADER));
     TRY(ensure_slots(c, 4096));
     const size_t smem = stencil_smem();
     int32_t *code = c->labels[BDR_LABELS_BADER];
     const double *rho = rho_ptr(c, BDR_RHO_REFERENCE);
+    if (!weights_symmetric(W_full))
+        return fail_msg("bader_calc: dist_mat[-d] != dist_mat[d]; not a step-length table");
+    const HalfWeights W = half_weights(W_full);
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_ROOTS));
         // vacuum comes from the fused tolerance test when the labels were made
@@ -203,8 +226,10 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges) {
     if (!c->labels[which]) return fail_msg("edge_find: label set is empty");
     TRY(ensure(&c->list, &c->list_cap, std::max<int64_t>(c->N / 16, 1024)));
     TRY(zero_counter(c, CNT_EDGES));
-    LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_candidates<TX, TY, TZ>), tile_grid(c->g), 256, 0,
-           c->labels[which], c->known, c->g, c->d_cnt + CNT_EDGES, c->list, c->list_cap);
+    const dim3 tg = tile_grid(c->g);
+    TRY(ensure_tile_flags(c, (size_t)tg.x * tg.y * tg.z));
+    LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_candidates<TX, TY, TZ>), tg, 256, 0, c->labels[which],
+           c->known, c->g, c->d_cnt + CNT_EDGES, c->list, c->list_cap, c->tile_flag);
     TRY(read_counters(c));
     int64_t n = (int64_t)c->h_cnt[CNT_EDGES];
     if (n > c->list_cap) {
@@ -220,8 +245,8 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges) {
         LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_confirm, blocks_for(n, 128), 128, 0,
                rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->list, n,
                c->d_cnt + CNT_NEWEDGE);
-        LAUNCH(c, BDR_K_EDGE_DILATE, (k_edge_dilate<TX, TY, TZ>), tile_grid(c->g), 256, 0, c->known,
-               c->g);
+        LAUNCH(c, BDR_K_EDGE_DILATE, (k_edge_dilate<TX, TY, TZ>), tg, 256, 0, c->known, c->g,
+               c->tile_flag);
         TRY(read_counters(c));
         confirmed = (int64_t)c->h_cnt[CNT_NEWEDGE];
     }
@@ -235,16 +260,32 @@ static int incremental_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *qu
     *queued = 0;
     c->list_n = 0;
     if (n_changed == 0) return 0;
-    TRY(ensure(&c->list, &c->list_cap, std::min<int64_t>(n_changed * 27, c->N)));
-    LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_mark, blocks_for(n_changed, 128), 128, 0, c->known, c->list2,
-           n_changed);
+    const int64_t cap = std::min<int64_t>(n_changed * 27, c->N);
+    TRY(ensure(&c->list3, &c->list3_cap, cap));
+    TRY(zero_counter(c, CNT_CENTRES));
+    if (n_changed * 64 > c->N) {
+        // a large round: marking with plain stores and one streaming compaction
+        // of the known array beats millions of contended byte exchanges
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_mark, blocks_for(n_changed * 27, 128), 128, 0,
+               c->labels[which], c->known, c->g, c->list2, n_changed);
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_compact_known, blocks_for(c->N, 256), 256, 0, c->known, c->N,
+               (int8_t)-6, c->d_cnt + CNT_CENTRES, c->list3, c->list3_cap);
+    } else {
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_collect, blocks_for(n_changed * 27, 128), 128, 0,
+               c->labels[which], c->known, c->g, c->list2, n_changed, c->d_cnt + CNT_CENTRES,
+               c->list3, c->list3_cap);
+    }
+    TRY(read_counters(c));
+    const int64_t nc = (int64_t)c->h_cnt[CNT_CENTRES];
+    if (nc > c->list3_cap) return fail_msg("incremental candidate list overflow");
+    if (nc == 0) return 0;
+    TRY(ensure(&c->list, &c->list_cap, nc));
     TRY(zero_counter(c, CNT_NEWEDGE));
-    LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_classify, blocks_for(n_changed * 27, 128), 128, 0,
-           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->list2, n_changed,
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_classify, blocks_for(nc, 128), 128, 0,
+           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->list3, nc,
            c->d_cnt + CNT_NEWEDGE, c->list, c->list_cap);
     TRY(read_counters(c));
     const int64_t nq = (int64_t)c->h_cnt[CNT_NEWEDGE];
-    if (nq > c->list_cap) return fail_msg("incremental queue overflow");
     if (nq > 0)
         LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_dilate, blocks_for(nq * 27, 128), 128, 0, c->known, c->g,
                c->list, nq);
@@ -517,7 +558,7 @@ int bdr_destroy(bdr_ctx *c) {
         if (c->labels[i]) cudaFree(c->labels[i]);
     for (void *p : {(void *)c->known, (void *)c->list, (void *)c->list2, (void *)c->list3,
                     (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
-                    (void *)c->d_sums, c->stage})
+                    (void *)c->d_sums, c->stage, (void *)c->tile_flag})
         if (p) cudaFree(p);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->pinned) cudaFreeHost(c->pinned);
