@@ -204,6 +204,7 @@ def main():
     ap.add_argument('--size', type=int, default=0, help='override: cubic N^3 single-GPU grid')
     ap.add_argument('--cpu-sample', type=int, default=176)
     ap.add_argument('--ref-sample', type=int, default=112)
+    ap.add_argument('--halo', type=int, default=8)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()

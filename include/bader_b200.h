@@ -171,6 +171,31 @@ int bdr_synth_general(bdr_ctx *ctx, int which, const double *lattice,
                       const double *frac_atoms, const double *amps,
                       const double *sigmas, int64_t n_atoms);
 
+/* ---- sharded runs: one slab handle per rank ---------- */
+/* A slab handle holds nx_window = owned + 2*halo x planes (y, z stay periodic).
+ * It stands for the reference's brick decomposition (thread_handlers.py:27-47):
+ * trajectories leaving the brick become provisional "exit" labels
+ * (methods.py:170-199) that the host resolves across ranks (utils.edge_assign,
+ * utils.py:263-280) -- here over NCCL.  All pointers below marked dev_ are
+ * device pointers (e.g. torch tensors' data_ptr()).                         */
+int bdr_slab_create(int device, int64_t nx_window, int64_t ny, int64_t nz, int halo,
+                    bdr_ctx **out);
+/* stencil + local pointer jumping on the window; leaves slot codes -2-s in the
+ * BADER labels: s < exit_base are exit-plane voxels (plane 0: s = y*nz+z,
+ * plane nx_window-1: s = ny*nz + y*nz+z), s >= exit_base are local maxima.  */
+int bdr_slab_seed(bdr_ctx *ctx, const double *dist_mat, int64_t *n_real, int64_t *exit_base);
+/* window-linear voxel index of each local maximum, int32[n_real]            */
+int bdr_slab_roots(bdr_ctx *ctx, int32_t *host_out, int64_t cap);
+/* first owned voxel (window-linear index, 0x7f7f7f7f if none) of every slot  */
+int bdr_slab_first_voxel(bdr_ctx *ctx, int64_t n_slots, int32_t *dev_out);
+/* slot codes -> global volume numbers through dev_rank[slot]                 */
+int bdr_slab_apply_rank(bdr_ctx *ctx, const int32_t *dev_rank);
+/* one full edge pass / one Jacobi trace launch over the owned edge voxels;
+ * escaped counts trajectories that left the trusted planes of the window    */
+int bdr_edge_pass(bdr_ctx *ctx, int which, int64_t *edges);
+int bdr_trace_pass(bdr_ctx *ctx, int which, const double *dist_mat, const double *T_grad,
+                   int64_t *changed, int64_t *escaped);
+
 /* ---- options ------------------------------------------------------------- */
 /* BDR_OPT_VERIFY_FIXED_POINT (default 0): bader_calc('neargrid') drives the
  * labels to quiescence with one full edge pass plus incremental rounds; with

@@ -50,6 +50,13 @@ SIGNATURES = {
     "bdr_trace_steps": ([_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
     "bdr_synth_separable": ([_p, _int, _p, _p, _p, _i64], _int),
     "bdr_synth_general": ([_p, _int, _p, _p, _p, _p, _i64], _int),
+    "bdr_slab_create": ([_int, _i64, _i64, _i64, _int, _pp], _int),
+    "bdr_slab_seed": ([_p, _p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
+    "bdr_slab_roots": ([_p, _p, _i64], _int),
+    "bdr_slab_first_voxel": ([_p, _i64, _p], _int),
+    "bdr_slab_apply_rank": ([_p, _p], _int),
+    "bdr_edge_pass": ([_p, _int, ctypes.POINTER(_i64)], _int),
+    "bdr_trace_pass": ([_p, _int, _p, _p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
     "bdr_set_option": ([_p, _int, _i64], _int),
     "bdr_device_ptr": ([_p, _int, _pp], _int),
 }

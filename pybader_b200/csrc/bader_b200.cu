@@ -45,6 +45,22 @@ static TGrad make_tgrad(const double *T) {
     return t;
 }
 
+static Window window_of(const bdr_ctx *c) {
+    Window w;
+    w.own_lo = (int)c->own_lo;
+    w.own_hi = (int)c->own_hi;
+    if (c->halo > 0) {
+        // classification needs labels two planes out, so positions are trusted
+        // on planes [2, nx-3] of the window
+        w.xlo = 2;
+        w.xhi = c->g.nx - 3;
+    } else {
+        w.xlo = -2147483647;
+        w.xhi = 2147483647;
+    }
+    return w;
+}
+
 static double *rho_ptr(bdr_ctx *c, int which) {
     int w = which;
     for (int hop = 0; hop < 3 && c->rho_alias[w] >= 0 && c->rho[w] == nullptr; ++hop)
@@ -141,7 +157,11 @@ static int rank_from_first(bdr_ctx *c, int64_t n, std::vector<int32_t> &order, b
 // ---------------------------------------------------------------------------
 // ongrid: stencil -> pointer codes -> resolve -> numbering
 // ---------------------------------------------------------------------------
-static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
+// slot numbering of a slab window: [0, 2*ny*nz) are the exit-plane voxels,
+// real maxima follow
+static int exit_base_of(const bdr_ctx *c) { return c->halo > 0 ? 2 * c->g.ny * c->g.nz : 0; }
+
+static int stencil_dev(bdr_ctx *c, const Weights &W_full, int64_t *n_real) {
     TRY(ensure_labels(c, BDR_LABELS_BADER));
     TRY(ensure_slots(c, 4096));
     const size_t smem = stencil_smem();
@@ -150,6 +170,7 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
     if (!weights_symmetric(W_full))
         return fail_msg("bader_calc: dist_mat[-d] != dist_mat[d]; not a step-length table");
     const HalfWeights W = half_weights(W_full);
+    const int xb = exit_base_of(c);
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_ROOTS));
         // vacuum comes from the fused tolerance test when the labels were made
@@ -157,15 +178,16 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
         // the label array itself (-1 entries)
         if (c->vac_mode == VAC_NONE)
             LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_NONE>), tile_grid(c->g, SX),
-                   256, smem, rho, code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap);
+                   256, smem, rho, code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap,
+                   xb);
         else if (c->vac_mode == VAC_TOL)
             LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_TOL>), tile_grid(c->g, SX),
                    256, smem, rho, code, c->g, W, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots,
-                   c->slots_cap);
+                   c->slots_cap, xb);
         else
             LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>),
                    tile_grid(c->g, SX), 256, smem, rho, code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS,
-                   c->roots, c->slots_cap);
+                   c->roots, c->slots_cap, xb);
         TRY(read_counters(c));
         const int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
         if (n <= c->slots_cap) break;
@@ -174,7 +196,15 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
         // (only voxel classes -1 / not -1 matter to the stencil pass)
         TRY(ensure_slots(c, n));
     }
-    const int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
+    *n_real = (int64_t)c->h_cnt[CNT_ROOTS];
+    return 0;
+}
+
+static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
+    if (c->halo > 0) return fail_msg("bader_calc: slab windows are driven through the bdr_slab_* entry points");
+    int64_t n = 0;
+    TRY(stencil_dev(c, W_full, &n));
+    int32_t *code = c->labels[BDR_LABELS_BADER];
     c->n_max = n;
     c->maxima.assign((size_t)n * 3, 0);
     if (n == 0) return 0;
@@ -243,8 +273,8 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges) {
     if (n > 0) {
         TRY(zero_counter(c, CNT_NEWEDGE));
         LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_confirm, blocks_for(n, 128), 128, 0,
-               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->list, n,
-               c->d_cnt + CNT_NEWEDGE);
+               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
+               c->list, n, c->d_cnt + CNT_NEWEDGE);
         LAUNCH(c, BDR_K_EDGE_DILATE, (k_edge_dilate<TX, TY, TZ>), tg, 256, 0, c->known, c->g,
                c->tile_flag);
         TRY(read_counters(c));
@@ -306,9 +336,10 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
     CU(cudaMemsetAsync(c->d_cnt + CNT_CHANGED, 0, sizeof(unsigned long long) * 2, c->stream));
     CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
     TRY(zero_counter(c, CNT_STEPS));
+    TRY(zero_counter(c, CNT_ESCAPED));
     LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n, 128), 128, 0,
-           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, W, T, c->list, n,
-           (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
+           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c), W, T,
+           c->list, n, (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
            c->list2_cap, c->list3, c->list3_cap, step_cap);
     TRY(read_counters(c));
     if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
@@ -323,8 +354,8 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
         for (int64_t o = 0; o < ov; o += batch) {
             const int64_t m = std::min(batch, ov - o);
             LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
-                   rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, W, T,
-                   c->list3 + o, m, (int32_t *)c->stage, c->d_cnt,
+                   rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
+                   W, T, c->list3 + o, m, (int32_t *)c->stage, c->d_cnt,
                    want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
                    (int32_t *)nullptr, (int64_t)0, step_cap);
         }
@@ -332,6 +363,8 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
         if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
     }
     *changed = (int64_t)c->h_cnt[CNT_CHANGED];
+    c->escaped = (int64_t)c->h_cnt[CNT_ESCAPED];
+    if (c->escaped && c->halo == 0) return fail_msg("trace: internal error (escape on a periodic grid)");
     c->trace_steps += (int64_t)c->h_cnt[CNT_STEPS];
     c->trace_voxels += n;
     return 0;
@@ -475,13 +508,16 @@ static int charge_sum_dev(bdr_ctx *c, int which_labels, int which_density, doubl
     double *q = c->d_sums;
     unsigned long long *cnt = reinterpret_cast<unsigned long long *>(c->d_sums + n);
     const int64_t per_block = 256 * 64;
-    const unsigned nb = blocks_for(c->N, (int)per_block);
+    const int64_t n_own = c->own_hi - c->own_lo;  // a slab sums its own voxels only
+    const unsigned nb = blocks_for(n_own, (int)per_block);
+    const int32_t *lab = c->labels[which_labels] + c->own_lo;
+    dens += c->own_lo;
     if (n <= SUM_BINS)
-        LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<true>, nb, 256, 0, dens, c->labels[which_labels],
-               c->N, (int)n, q, cnt, per_block);
+        LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<true>, nb, 256, 0, dens, lab, n_own, (int)n, q, cnt,
+               per_block);
     else
-        LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<false>, nb, 256, 0, dens, c->labels[which_labels],
-               c->N, (int)n, q, cnt, per_block);
+        LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<false>, nb, 256, 0, dens, lab, n_own, (int)n, q, cnt,
+               per_block);
     std::vector<double> hq((size_t)n);
     std::vector<unsigned long long> hc((size_t)n);
     CU(cudaMemcpyAsync(hq.data(), q, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -534,6 +570,8 @@ int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out) {
     c->device = device;
     c->g = Grid{(int)nx, (int)ny, (int)nz};
     c->N = N;
+    c->own_lo = 0;
+    c->own_hi = N;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&c->d_cnt, sizeof(unsigned long long) * CNT_NUM));
     CU(cudaMemsetAsync(c->d_cnt, 0, sizeof(unsigned long long) * CNT_NUM, c->stream));
@@ -545,6 +583,76 @@ int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out) {
     CU(cudaFuncSetAttribute(k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
     *out = c;
+    return 0;
+}
+
+int bdr_slab_create(int device, int64_t nx_window, int64_t ny, int64_t nz, int halo, bdr_ctx **out) {
+    if (halo < 3) return fail_msg("bdr_slab_create: halo must be at least 3 planes");
+    if (nx_window <= 2 * (int64_t)halo) return fail_msg("bdr_slab_create: window thinner than its halos");
+    TRY(bdr_create(device, nx_window, ny, nz, out));
+    bdr_ctx *c = *out;
+    c->halo = halo;
+    c->own_lo = (int64_t)halo * ny * nz;
+    c->own_hi = (nx_window - halo) * ny * nz;
+    return 0;
+}
+
+int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *exit_base) {
+    TRY(check(c));
+    if (c->halo == 0) return fail_msg("bdr_slab_seed: not a slab handle");
+    if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_slab_seed: density not set");
+    const Weights W = make_weights(dist_mat);
+    int64_t n = 0;
+    TRY(stencil_dev(c, W, &n));
+    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 256), 256, 0, c->labels[BDR_LABELS_BADER],
+           c->N, (int32_t *)nullptr);
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_max = n;
+    if (n_real) *n_real = n;
+    if (exit_base) *exit_base = exit_base_of(c);
+    return 0;
+}
+
+int bdr_slab_first_voxel(bdr_ctx *c, int64_t n_slots, int32_t *dev_out) {
+    TRY(check(c));
+    CU(cudaMemsetAsync(dev_out, 0x7f, (size_t)n_slots * sizeof(int32_t), c->stream));
+    LAUNCH(c, BDR_K_FIRST, k_first_voxel_slots, blocks_for(c->own_hi - c->own_lo, 256), 256, 0,
+           c->labels[BDR_LABELS_BADER], (int)c->own_lo, (int)c->own_hi, dev_out);
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_slab_apply_rank(bdr_ctx *c, const int32_t *dev_rank) {
+    TRY(check(c));
+    LAUNCH(c, BDR_K_RELABEL, k_relabel_slots, blocks_for(c->N, 1024), 256, 0,
+           c->labels[BDR_LABELS_BADER], c->N, dev_rank);
+    c->vac_mode = VAC_LABELS;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_slab_roots(bdr_ctx *c, int32_t *host_out, int64_t cap) {
+    TRY(check(c));
+    if (cap < c->n_max) return fail_msg("bdr_slab_roots: buffer too small");
+    if (c->n_max)
+        CU(cudaMemcpy(host_out, c->roots, (size_t)c->n_max * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int bdr_edge_pass(bdr_ctx *c, int which, int64_t *edges) { return bdr_edge_find(c, which, edges); }
+
+int bdr_trace_pass(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
+                   int64_t *changed, int64_t *escaped) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_trace_pass: bad label set");
+    if (!c->known) return fail_msg("bdr_trace_pass: run bdr_edge_pass first");
+    const Weights W = make_weights(dist_mat);
+    const TGrad T = make_tgrad(T_grad);
+    int64_t ch = 0;
+    TRY(trace_dev(c, which, W, T, &ch, false));
+    CU(cudaStreamSynchronize(c->stream));
+    if (changed) *changed = ch;
+    if (escaped) *escaped = c->escaped;
     return 0;
 }
 

@@ -68,6 +68,7 @@ enum {
     CNT_OVERFLOW = 7,  // trace paths that outgrew the register-file path buffer
     CNT_ERROR = 8,     // trace step cap exceeded
     CNT_VACUUM = 9,    // vacuum voxel count
+    CNT_ESCAPED = 11,  // trajectories that left the trusted planes of a slab window
     CNT_STEPS = 10,    // trajectory steps taken by the trace kernel (accounting)
     CNT_NUM = 16
 };
@@ -84,6 +85,9 @@ struct bdr_ctx {
     cudaStream_t stream = nullptr;
     bdr::Grid g{0, 0, 0};
     int64_t N = 0;
+    int halo = 0;               // slab windows: extra x planes on each side (0 = periodic grid)
+    int64_t own_lo = 0, own_hi = 0;  // owned linear index range
+    int64_t escaped = 0;        // trajectories that left the trusted planes in the last trace
 
     double *rho[3] = {nullptr, nullptr, nullptr};
     int rho_alias[3] = {-1, 0, 0};  // -1: owns storage (or empty); k: alias of slot k

@@ -1,0 +1,432 @@
+"""Sharded (multi-GPU) Bader analysis: one process per GPU, x-slabs, NCCL.
+
+The reference parallelises by cutting the volume into bricks, letting every
+brick run on its own and resolving trajectories that leave a brick afterwards
+(thread_handlers.py:27-75; "edge" labels methods.py:170-199; utils.edge_assign
+utils.py:263-280; renumbering utils.volume_offset utils.py:497-510).  The same
+idea, restated for GPUs:
+
+* the grid is cut into contiguous slabs along the slowest storage axis (x);
+  rank r owns planes [x0_r, x1_r) and keeps `halo` extra planes on each side;
+* every rank runs the single-GPU kernels on its window.  The outermost plane
+  on each side is an *exit*: an ascent path reaching it stops there;
+* exits are resolved between neighbours by exchanging one plane of resolved
+  root ids per direction, iterated until no exit is left (<= world rounds);
+* volumes are numbered globally by their first voxel (C order), exactly like
+  the single-GPU path, from an all-gather of (root id, first voxel) pairs;
+* refinement runs full Jacobi passes; after each pass the owned boundary
+  planes of the label array are sent to the neighbours' halos.
+
+`torch.distributed` is the plumbing (process group, send/recv, all-reduce); all
+per-voxel work is done by libbader_b200.so kernels through `SlabBackend`.
+The protocol code below only touches plane- and root-sized tensors and is
+device agnostic, so tests drive it on CPU over gloo with a model backend.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+UNRESOLVED = -1
+VACUUM = -2
+NO_VOXEL = 0x7f7f7f7f
+
+
+def slab_bounds(nx, world):
+    """contiguous split of nx planes; the first nx % world ranks get one more"""
+    base, rem = divmod(nx, world)
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < rem else 0))
+    return bounds
+
+
+class Comm:
+    """ring neighbours over torch.distributed (NCCL on GPUs, gloo in CPU tests)"""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.prev = (self.rank - 1) % self.world
+        self.next = (self.rank + 1) % self.world
+
+    def ring_exchange(self, send_up, send_down, recv_lo, recv_hi):
+        """send_up -> next rank's recv_lo, send_down -> prev rank's recv_hi"""
+        if self.world == 1:
+            recv_lo.copy_(send_up)
+            recv_hi.copy_(send_down)
+            return
+        ops = [dist.P2POp(dist.isend, send_up, self.next, self.group, tag=1),
+               dist.P2POp(dist.isend, send_down, self.prev, self.group, tag=2),
+               dist.P2POp(dist.irecv, recv_lo, self.prev, self.group, tag=1),
+               dist.P2POp(dist.irecv, recv_hi, self.next, self.group, tag=2)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def allreduce_sum(self, value, device):
+        t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
+    def allreduce_max(self, value, device):
+        t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def allgather_padded(self, t, pad_value):
+        """all-gather of 1-D tensors of different lengths (padded to the max)"""
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.group)
+        m = int(n.item())
+        buf = torch.full((m,), pad_value, dtype=t.dtype, device=t.device)
+        buf[:t.shape[0]] = t
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(out, buf, group=self.group)
+        return torch.cat(out)
+
+
+class ShardedBader:
+    """The cross-rank protocol.  `backend` does the per-voxel work on this
+    rank's window and exposes window-shaped torch tensors (see SlabBackend)."""
+
+    def __init__(self, global_shape, comm, backend_factory, halo=8):
+        self.comm = comm
+        self.shape = tuple(int(s) for s in global_shape)
+        nx, self.ny, self.nz = self.shape
+        self.halo = int(halo)
+        b = slab_bounds(nx, comm.world)
+        self.x0, self.x1 = b[comm.rank], b[comm.rank + 1]
+        self.nxl = self.x1 - self.x0
+        if min(b[i + 1] - b[i] for i in range(comm.world)) < self.halo:
+            raise ValueError("slabs thinner than the halo: use fewer ranks or a smaller halo")
+        self.W = self.nxl + 2 * self.halo
+        self.plane = self.ny * self.nz
+        # global x of every window plane (periodic)
+        self.window_x = (np.arange(self.W) + self.x0 - self.halo) % nx
+        self.backend = backend_factory((self.W, self.ny, self.nz), self.halo)
+        self.maxima = np.zeros((0, 3), dtype=np.int64)
+
+    # ---- helpers -----------------------------------------------------------
+    def _gid_of_window_index(self, widx):
+        """window-linear voxel index -> global linear voxel index (int64)"""
+        xw = torch.div(widx, self.plane, rounding_mode='floor')
+        rest = widx - xw * self.plane
+        wx = torch.as_tensor(self.window_x, dtype=torch.int64, device=widx.device)
+        return wx[xw] * self.plane + rest
+
+    def exchange_halo(self, t):
+        """fill the halo planes of a window tensor [W, ny, nz] from the owners"""
+        H, n = self.halo, self.nxl
+        up = t[n:n + H].contiguous()        # my top owned planes -> next's low halo
+        down = t[H:2 * H].contiguous()      # my bottom owned planes -> prev's high halo
+        lo = torch.empty_like(up)
+        hi = torch.empty_like(down)
+        self.comm.ring_exchange(up, down, lo, hi)
+        t[:H].copy_(lo)
+        t[self.W - H:].copy_(hi)
+
+    # ---- ongrid: seed, exits, numbering -----------------------------------
+    def ongrid(self, dist_mat):
+        be, H, P = self.backend, self.halo, self.plane
+        n_real, exit_base = be.seed(dist_mat)
+        codes = be.labels()                      # int32 [W, ny, nz]: -1 vacuum, -2-s slots
+        dev = codes.device
+        n_slots = exit_base + n_real
+        # slot -> global root id
+        G = torch.full((n_slots,), UNRESOLVED, dtype=torch.int64, device=dev)
+        if n_real:
+            G[exit_base:] = self._gid_of_window_index(be.roots().to(torch.int64))
+
+        def export(plane_index):
+            c = codes[plane_index].reshape(-1).to(torch.int64)
+            out = torch.full_like(c, VACUUM)
+            s = -2 - c
+            sel = c <= -2
+            out[sel] = G[s[sel]]
+            return out
+
+        for _ in range(self.comm.world + 1):
+            up, down = export(self.nxl), export(2 * H - 1)
+            lo, hi = torch.empty_like(up), torch.empty_like(down)
+            self.comm.ring_exchange(up, down, lo, hi)
+            G[:P] = lo
+            G[P:2 * P] = hi
+            pending = int(((up == UNRESOLVED).sum() + (down == UNRESOLVED).sum()).item())
+            if self.comm.allreduce_sum(pending, dev) == 0:
+                break
+        else:
+            raise RuntimeError("exit resolution did not converge")
+        # one more hop is implied: exits used by owned voxels are now resolved,
+        # because every plane a neighbour needs from me was exported resolved
+
+        # first owned voxel of every slot -> per root id
+        first_w = be.first_voxel(n_slots).to(torch.int64)          # window-linear or NO_VOXEL
+        used = first_w != NO_VOXEL
+        if bool((G[used] == UNRESOLVED).any()):
+            raise RuntimeError("an owned voxel ends in an unresolved exit")
+        sel = used & (G >= 0)
+        gid_l = G[sel]
+        first_l = self._gid_of_window_index(first_w[sel])
+        gids = self.comm.allgather_padded(gid_l, -1)
+        firsts = self.comm.allgather_padded(first_l, -1)
+        keep = gids >= 0
+        gids, firsts = gids[keep], firsts[keep]
+        uniq, inv = torch.unique(gids, return_inverse=True)
+        first_u = torch.full((uniq.shape[0],), torch.iinfo(torch.int64).max, dtype=torch.int64,
+                             device=dev)
+        first_u.scatter_reduce_(0, inv, firsts, reduce='amin')
+        order = torch.argsort(first_u)              # volume number -> index into uniq
+        number_of = torch.empty_like(order)
+        number_of[order] = torch.arange(order.shape[0], device=dev)
+        # slot -> volume number (vacuum and unused exits -> -1)
+        rank_lut = torch.full((max(n_slots, 1),), -1, dtype=torch.int32, device=dev)
+        ok = G >= 0
+        if uniq.shape[0]:
+            pos = torch.searchsorted(uniq, G[ok])
+            pos = pos.clamp(max=uniq.shape[0] - 1)
+            hit = uniq[pos] == G[ok]
+            vals = torch.where(hit, number_of[pos], torch.full_like(pos, -1)).to(torch.int32)
+            rank_lut[ok] = vals
+        be.apply_rank(rank_lut)
+        mg = uniq[order].cpu().numpy()
+        self.maxima = np.stack([mg // P, (mg // self.nz) % self.ny, mg % self.nz], axis=1)
+        return self.maxima
+
+    # ---- refinement ---------------------------------------------------------
+    def refine(self, dist_mat, T_grad, iters=-1):
+        """full ('all'-mode) Jacobi passes until nothing changes anywhere, or
+        `iters` passes; returns [(edges, changed)] with global counts"""
+        be, dev = self.backend, self.backend.labels().device
+        history = []
+        it = 0
+        while iters < 0 or it < iters:
+            self.exchange_halo(be.labels())
+            edges = be.edge_pass()
+            changed, escaped = be.trace_pass(dist_mat, T_grad)
+            if self.comm.allreduce_sum(escaped, dev):
+                raise RuntimeError("a trajectory left the slab halo: raise `halo`")
+            edges = self.comm.allreduce_sum(edges, dev)
+            changed = self.comm.allreduce_sum(changed, dev)
+            history.append((edges, changed))
+            it += 1
+            if changed == 0 or edges == 0:
+                break
+        self.exchange_halo(be.labels())
+        return history
+
+    def neargrid(self, dist_mat, T_grad):
+        self.ongrid(dist_mat)
+        self.refine(dist_mat, T_grad, -1)
+        return self.maxima
+
+    def charge_sum(self, n, voxel_volume, which_density=0):
+        be = self.backend
+        q, v = be.charge_sum(n, voxel_volume, which_density)
+        t = torch.as_tensor(np.stack([q, v]), device=be.labels().device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.comm.group)
+        t = t.cpu().numpy()
+        return t[0], t[1]
+
+    def owned_labels(self):
+        return self.backend.labels()[self.halo:self.halo + self.nxl]
+
+
+# ---------------------------------------------------------------------------
+class _DevArray:
+    """zero-copy torch view of device memory owned by the C library"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3}
+
+
+class SlabBackend:
+    """per-rank kernels through the C ABI (bdr_slab_*), window tensors as
+    zero-copy torch views"""
+
+    def __init__(self, window_shape, halo, device=0):
+        from . import _lib
+        from ._lib import check
+        self.check = check
+        self.lib = _lib.load()
+        self.shape = tuple(window_shape)
+        self.halo = halo
+        self.device = torch.device('cuda', device)
+        h = ctypes.c_void_p()
+        check(self.lib.bdr_slab_create(int(device), *self.shape, int(halo), ctypes.byref(h)))
+        self.h = h
+        self.N = int(np.prod(self.shape))
+        self.n_real = 0
+        self.exit_base = 0
+        self._labels = None
+        self._roots = None
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.bdr_destroy(self.h)
+            self.h = None
+
+    def _ptr(self, what):
+        p = ctypes.c_void_p()
+        self.check(self.lib.bdr_device_ptr(self.h, what, ctypes.byref(p)))
+        return p.value
+
+    def density(self, which=0):
+        return torch.as_tensor(_DevArray(self._ptr(which), self.shape, '<f8'), device=self.device)
+
+    def alloc_density(self, which=0):
+        """make sure slot `which` has storage and return its window view"""
+        zeros = np.zeros(1)
+        # a 1-atom zero table allocates the slot without a host-sized upload
+        z = [np.zeros((1, n)) for n in self.shape]
+        self.check(self.lib.bdr_synth_separable(self.h, which, z[0].ctypes.data, z[1].ctypes.data,
+                                                z[2].ctypes.data, 1))
+        del zeros
+        return self.density(which)
+
+    def synth_separable(self, which, tx, ty, tz):
+        tx, ty, tz = (np.ascontiguousarray(t, dtype=np.float64) for t in (tx, ty, tz))
+        self.check(self.lib.bdr_synth_separable(self.h, which, tx.ctypes.data, ty.ctypes.data,
+                                                tz.ctypes.data, tx.shape[0]))
+
+    def clear_labels(self):
+        self.check(self.lib.bdr_clear_labels(self.h, 0))
+        self._labels = None
+
+    def vacuum_assign(self, tol, dV):
+        q, v = ctypes.c_double(0), ctypes.c_double(0)
+        self.check(self.lib.bdr_vacuum_assign(self.h, float(tol), float(dV), 0, ctypes.byref(q),
+                                              ctypes.byref(v)))
+        return q.value, v.value
+
+    def labels(self):
+        if self._labels is None:
+            self._labels = torch.as_tensor(_DevArray(self._ptr(3), self.shape, '<i4'),
+                                           device=self.device)
+        return self._labels
+
+    def seed(self, dist_mat):
+        d = np.ascontiguousarray(dist_mat, dtype=np.float64)
+        n, xb = ctypes.c_int64(0), ctypes.c_int64(0)
+        self.check(self.lib.bdr_slab_seed(self.h, d.ctypes.data, ctypes.byref(n), ctypes.byref(xb)))
+        self.n_real, self.exit_base = n.value, xb.value
+        return self.n_real, self.exit_base
+
+    def roots(self):
+        out = np.zeros(max(self.n_real, 1), dtype=np.int32)
+        self.check(self.lib.bdr_slab_roots(self.h, out.ctypes.data, out.shape[0]))
+        return torch.as_tensor(out[:self.n_real], device=self.device)
+
+    def first_voxel(self, n_slots):
+        out = torch.empty(max(n_slots, 1), dtype=torch.int32, device=self.device)
+        self.check(self.lib.bdr_slab_first_voxel(self.h, int(n_slots), out.data_ptr()))
+        return out[:n_slots]
+
+    def apply_rank(self, rank_lut):
+        rank_lut = rank_lut.contiguous()
+        torch.cuda.synchronize(self.device)
+        self.check(self.lib.bdr_slab_apply_rank(self.h, rank_lut.data_ptr()))
+
+    def edge_pass(self):
+        torch.cuda.synchronize(self.device)
+        e = ctypes.c_int64(0)
+        self.check(self.lib.bdr_edge_pass(self.h, 0, ctypes.byref(e)))
+        return e.value
+
+    def trace_pass(self, dist_mat, T_grad):
+        d = np.ascontiguousarray(dist_mat, dtype=np.float64)
+        t = np.ascontiguousarray(T_grad, dtype=np.float64)
+        ch, esc = ctypes.c_int64(0), ctypes.c_int64(0)
+        self.check(self.lib.bdr_trace_pass(self.h, 0, d.ctypes.data, t.ctypes.data,
+                                           ctypes.byref(ch), ctypes.byref(esc)))
+        return ch.value, esc.value
+
+    def charge_sum(self, n, dV, which_density=0):
+        q, v = np.zeros(n), np.zeros(n)
+        self.check(self.lib.bdr_charge_sum(self.h, 0, which_density, float(dV), n, q.ctypes.data,
+                                           v.ctypes.data))
+        return q, v
+
+    def timer_start(self):
+        self.check(self.lib.bdr_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double(0)
+        self.check(self.lib.bdr_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = ctypes.c_int64(0)
+        self.check(self.lib.bdr_launch_count(self.h, ctypes.byref(n)))
+        return n.value
+
+
+# ---------------------------------------------------------------------------
+def bench(args, rank, world, local):
+    """bench.py's N > 1 arm: weak scaling, 2^30 voxels per GPU, x-slabs."""
+    import json
+    import os
+    import sys
+    import time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench as B
+    from . import build, geometry as geo, synth
+    build.build()
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', local))
+    comm = Comm()
+    shape = B.SHAPES[world] if not args.size else (args.size * world, args.size, args.size)
+    case, cells = B.workload_case(shape)
+    dm = geo.distance_matrix(case['lattice'], shape)
+    T = geo.T_grad(case['lattice'], shape)
+    sb = ShardedBader(shape, comm, lambda ws, h: SlabBackend(ws, h, device=local), halo=args.halo)
+    tx, ty, tz = synth.separable_tables(case)
+    sb.backend.synth_separable(0, np.ascontiguousarray(tx[:, sb.window_x]), ty, tz)
+    N = int(np.prod(shape))
+
+    def step():
+        sb.backend.clear_labels()
+        sb.neargrid(dm, T)                 # ongrid seed + exits + numbering + passes to quiescence
+        return sb.refine(dm, T, 2)         # the caller's refine(): full pass(es)
+
+    for _ in range(args.warmup):
+        hist = step()
+    clocks = B.ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0 = sb.backend.launch_count()
+    sb.backend.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hist = step()
+    ms = sb.backend.timer_stop()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    launches = sb.backend.launch_count() - l0
+    ms = comm.allreduce_max(ms, torch.device('cuda', local))
+    launches = comm.allreduce_sum(launches, torch.device('cuda', local))
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        out = {
+            "metric": B.METRIC, "value": N / (ms_per_step * 1e-3), "unit": B.UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": B.workload_name(shape), "atoms": len(case['amps']),
+                       "maxima": int(sb.maxima.shape[0]), "method": "neargrid",
+                       "refine_method": "neargrid", "refine_mode": ["all", 2],
+                       "parallelism": f"{world} x-slabs, halo {args.halo} planes, NCCL ring exchange",
+                       "l2": "per-GPU inputs are far larger than the 126 MB L2; no flush"},
+            "roofline": None, "cpu_baseline": None,
+            "e2e": None, "gpu_launches": launches, "clocks": clocks.stop(),
+            "wall_ms_per_step": wall / args.steps, "refine_history_last_step": hist,
+        }
+        print(json.dumps(out))
+    dist.destroy_process_group()

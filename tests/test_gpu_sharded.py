@@ -1,0 +1,84 @@
+"""2-GPU check of the sharded path against the single-GPU path (needs >= 2
+visible GPUs; skipped otherwise)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _case():
+    from pybader_b200 import geometry as geo, synth
+    c = synth.case_rocksalt(96, cells=2, offset=0.13, a=5.64)
+    c['shape'] = (96, 64, 80)
+    rho, atoms = synth.make(c)
+    return rho, geo.distance_matrix(c['lattice'], rho.shape), geo.T_grad(c['lattice'], rho.shape), \
+        geo.voxel_volume(c['lattice'], rho.shape)
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        from pybader_b200.sharded import Comm, ShardedBader, SlabBackend
+        rho, dm, T, dV = _case()
+        sb = ShardedBader(rho.shape, Comm(), lambda ws, h: SlabBackend(ws, h, device=rank), halo=8)
+        win = np.ascontiguousarray(rho[sb.window_x])
+        sb.backend.check(sb.backend.lib.bdr_upload_density(sb.backend.h, 0, win.ctypes.data))
+        sb.backend.clear_labels()
+        mx = sb.ongrid(dm)
+        lab_on = sb.owned_labels().cpu().numpy().copy()
+        hist = sb.refine(dm, T, -1)
+        lab_ng = sb.owned_labels().cpu().numpy().copy()
+        q, v = sb.charge_sum(mx.shape[0], dV)
+        np.savez(os.path.join(out, f'r{rank}.npz'), maxima=mx, lab_on=lab_on, lab_ng=lab_ng,
+                 hist=np.array(hist), q=q, v=v)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_labels_equal_single_gpu(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pybader_b200 import build
+    build.build()
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    from pybader_b200.engine import Engine, LABELS_BADER
+    rho, dm, T, dV = _case()
+    e = Engine(rho.shape)
+    e.upload_density(0, rho)
+    e.clear_labels()
+    mx = e.bader_calc('ongrid', dm, T)
+    ref_on = e.download_labels(LABELS_BADER, np.int32)
+    hist = e.refine(LABELS_BADER, 'all', -1, dm, T)
+    ref_ng = e.download_labels(LABELS_BADER, np.int32)
+    q, v = np.zeros(mx.shape[0]), np.zeros(mx.shape[0])
+    e.charge_sum(LABELS_BADER, 0, dV, q, v)
+    e.close()
+    parts = [np.load(os.path.join(str(tmp_path), f'r{r}.npz')) for r in range(2)]
+    np.testing.assert_array_equal(parts[0]['maxima'], mx)
+    np.testing.assert_array_equal(np.concatenate([p['lab_on'] for p in parts]), ref_on)
+    np.testing.assert_array_equal(np.concatenate([p['lab_ng'] for p in parts]), ref_ng)
+    assert [tuple(h) for h in parts[0]['hist']] == hist
+    np.testing.assert_allclose(parts[0]['q'], q, rtol=1e-12)
+    np.testing.assert_allclose(parts[0]['v'], v, rtol=1e-12)
