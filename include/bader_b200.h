@@ -205,6 +205,11 @@ int bdr_trace_pass(bdr_ctx *ctx, int which, const double *dist_mat, const double
 enum { BDR_OPT_VERIFY_FIXED_POINT = 0 };
 int bdr_set_option(bdr_ctx *ctx, int option, int64_t value);
 
+/* self test: the trace kernel divides three gradient components by one
+ * maximum through a shared reciprocal; this checks that sequence against the
+ * hardware IEEE division on n pseudo-random operand pairs                    */
+int bdr_selftest_div(bdr_ctx *ctx, int64_t n, uint64_t seed, int64_t *mismatches);
+
 /* device pointers, for torch.distributed halo plumbing in the sharded path  */
 int bdr_device_ptr(bdr_ctx *ctx, int what, void **ptr);
 

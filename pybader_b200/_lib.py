@@ -57,6 +57,7 @@ SIGNATURES = {
     "bdr_slab_apply_rank": ([_p, _p], _int),
     "bdr_edge_pass": ([_p, _int, ctypes.POINTER(_i64)], _int),
     "bdr_trace_pass": ([_p, _int, _p, _p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
+    "bdr_selftest_div": ([_p, _i64, ctypes.c_uint64, ctypes.POINTER(_i64)], _int),
     "bdr_set_option": ([_p, _int, _i64], _int),
     "bdr_device_ptr": ([_p, _int, _pp], _int),
 }

@@ -9,6 +9,7 @@ thread_local std::string g_err;
 
 constexpr int TX = 8, TY = 8, TZ = 32;   // edge-pass tile (z fastest)
 constexpr int SX = 15;                   // stencil tile depth along x (the marched axis)
+constexpr int EDGE_CX = 32;              // planes one CTA of the edge pass streams through
 
 static dim3 tile_grid(const Grid &g, int tx = TX) {
     return dim3((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + tx - 1) / tx);
@@ -86,13 +87,12 @@ static int ensure_known(bdr_ctx *c) {
     CU(cudaMalloc((void **)&c->known, (size_t)c->N));
     return 0;
 }
-static int ensure_tile_flags(bdr_ctx *c, size_t n) {
-    if (c->tile_flag_n >= n) return 0;
-    if (c->tile_flag) cudaFree(c->tile_flag);
-    c->tile_flag = nullptr;
-    c->tile_flag_n = 0;
-    CU(cudaMalloc((void **)&c->tile_flag, n));
-    c->tile_flag_n = n;
+static int ensure_bits(bdr_ctx *c) {
+    if (c->ebits) return 0;
+    c->nzw = (c->g.nz + 31) / 32;
+    const size_t words = (size_t)c->g.nx * c->g.ny * c->nzw;
+    CU(cudaMalloc((void **)&c->ebits, 2 * words * sizeof(uint32_t)));
+    c->vbits = c->ebits + words;
     return 0;
 }
 static int ensure_rho(bdr_ctx *c, int which) {
@@ -209,7 +209,8 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
     c->maxima.assign((size_t)n * 3, 0);
     if (n == 0) return 0;
     CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
-    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 256), 256, 0, code, c->N, c->minidx);
+    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, code, c->N, c->minidx,
+           getenv("BDR_RESOLVE_MODE") ? atoi(getenv("BDR_RESOLVE_MODE")) : 0);
     std::vector<int32_t> order;
     TRY(rank_from_first(c, n, order, nullptr));
     std::vector<int32_t> roots((size_t)n);
@@ -253,34 +254,48 @@ static int renumber_dev(bdr_ctx *c, int which) {
 // ---------------------------------------------------------------------------
 static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges) {
     TRY(ensure_known(c));
+    TRY(ensure_bits(c));
     if (!c->labels[which]) return fail_msg("edge_find: label set is empty");
     TRY(ensure(&c->list, &c->list_cap, std::max<int64_t>(c->N / 16, 1024)));
-    TRY(zero_counter(c, CNT_EDGES));
-    const dim3 tg = tile_grid(c->g);
-    TRY(ensure_tile_flags(c, (size_t)tg.x * tg.y * tg.z));
-    LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_candidates<TX, TY, TZ>), tg, 256, 0, c->labels[which],
-           c->known, c->g, c->d_cnt + CNT_EDGES, c->list, c->list_cap, c->tile_flag);
-    TRY(read_counters(c));
-    int64_t n = (int64_t)c->h_cnt[CNT_EDGES];
-    if (n > c->list_cap) {
-        TRY(ensure(&c->list, &c->list_cap, n));
+    const dim3 grid((c->g.nz + 127) / 128, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
+    LAUNCH(c, BDR_K_EDGE_FLAG, k_edge_bits<EDGE_CX>, grid, 256, 0, c->labels[which], c->g, c->ebits,
+           c->vbits, c->nzw);
+    int64_t n = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_EDGES));
-        LAUNCH(c, BDR_K_EDGE_FLAG, k_compact_known, blocks_for(c->N, 256), 256, 0, c->known, c->N,
-               (int8_t)-2, c->d_cnt + CNT_EDGES, c->list, c->list_cap);
-    }
-    c->list_n = n;  // includes tomb-stoned maxima; the trace kernel skips them
-    int64_t confirmed = 0;
-    if (n > 0) {
-        TRY(zero_counter(c, CNT_NEWEDGE));
-        LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_confirm, blocks_for(n, 128), 128, 0,
-               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
-               c->list, n, c->d_cnt + CNT_NEWEDGE);
-        LAUNCH(c, BDR_K_EDGE_DILATE, (k_edge_dilate<TX, TY, TZ>), tg, 256, 0, c->known, c->g,
-               c->tile_flag);
+        LAUNCH(c, BDR_K_EDGE_DILATE, k_edge_known,
+               dim3((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + 7) / 8), 256, 0, c->ebits, c->vbits,
+               c->known, c->g, c->nzw, c->d_cnt + CNT_EDGES, c->list, c->list_cap);
         TRY(read_counters(c));
-        confirmed = (int64_t)c->h_cnt[CNT_NEWEDGE];
+        n = (int64_t)c->h_cnt[CNT_EDGES];
+        if (n <= c->list_cap) break;
+        TRY(ensure(&c->list, &c->list_cap, n));  // the list overflowed: grow it and redo the cheap half
     }
-    *edges = confirmed;
+    c->list_n = n;  // every candidate of the window; the trace kernel skips what it does not own
+    *edges = 0;
+    if (n == 0) return 0;
+    // density half of the classification: drop the candidates that are maxima
+    TRY(ensure(&c->list3, &c->list3_cap, 4096));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        TRY(zero_counter(c, CNT_NEWEDGE));
+        TRY(zero_counter(c, CNT_CENTRES));
+        LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_confirm, blocks_for(n, 128), 128, 0,
+               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->g, window_of(c), c->list, n,
+               c->d_cnt + CNT_NEWEDGE, c->d_cnt + CNT_CENTRES, c->list3, c->list3_cap);
+        TRY(read_counters(c));
+        if ((int64_t)c->h_cnt[CNT_CENTRES] <= c->list3_cap) break;
+        TRY(ensure(&c->list3, &c->list3_cap, (int64_t)c->h_cnt[CNT_CENTRES]));
+    }
+    *edges = (int64_t)c->h_cnt[CNT_NEWEDGE];
+    const int64_t nf = (int64_t)c->h_cnt[CNT_CENTRES];
+    if (nf > 0) {
+        LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_fix_clear, blocks_for(nf, 128), 128, 0, c->ebits, c->g,
+               c->nzw, c->list, c->list3, nf);
+        LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_fix_known, blocks_for(nf * 27, 128), 128, 0, c->ebits,
+               c->vbits, c->known, c->g, c->nzw, c->list, c->list3, nf);
+        LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_fix_tomb, blocks_for(nf, 128), 128, 0, c->list, c->list3,
+               nf);
+    }
     return 0;
 }
 
@@ -337,9 +352,14 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
     CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
     TRY(zero_counter(c, CNT_STEPS));
     TRY(zero_counter(c, CNT_ESCAPED));
-    LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n, 128), 128, 0,
+    // list entries per warp: lanes refill from their warp's chunk, so longer chunks
+    // hide the spread of trajectory lengths; short lists keep every SM busy instead
+    int chunk = 32 * (int)std::min<int64_t>(16, std::max<int64_t>(1, n / (32 * 8192)));
+    if (getenv("BDR_TRACE_CHUNK")) chunk = std::min(chunk, atoi(getenv("BDR_TRACE_CHUNK")));
+    const int64_t n_warps = (n + chunk - 1) / chunk;
+    LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
            rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c), W, T,
-           c->list, n, (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
+           c->list, n, chunk, (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
            c->list2_cap, c->list3, c->list3_cap, step_cap);
     TRY(read_counters(c));
     if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
@@ -355,7 +375,7 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
             const int64_t m = std::min(batch, ov - o);
             LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
                    rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
-                   W, T, c->list3 + o, m, (int32_t *)c->stage, c->d_cnt,
+                   W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt,
                    want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
                    (int32_t *)nullptr, (int64_t)0, step_cap);
         }
@@ -604,8 +624,8 @@ int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *
     const Weights W = make_weights(dist_mat);
     int64_t n = 0;
     TRY(stencil_dev(c, W, &n));
-    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 256), 256, 0, c->labels[BDR_LABELS_BADER],
-           c->N, (int32_t *)nullptr);
+    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, c->labels[BDR_LABELS_BADER],
+           c->N, (int32_t *)nullptr, 0);
     CU(cudaStreamSynchronize(c->stream));
     c->n_max = n;
     if (n_real) *n_real = n;
@@ -666,7 +686,7 @@ int bdr_destroy(bdr_ctx *c) {
         if (c->labels[i]) cudaFree(c->labels[i]);
     for (void *p : {(void *)c->known, (void *)c->list, (void *)c->list2, (void *)c->list3,
                     (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
-                    (void *)c->d_sums, c->stage, (void *)c->tile_flag})
+                    (void *)c->d_sums, c->stage, (void *)c->ebits})
         if (p) cudaFree(p);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -926,8 +946,8 @@ int bdr_surface_distance(bdr_ctx *c, int which, const double *lattice, const dou
     CU(cudaMemcpyAsync(d_best, best.data(), (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice,
                        c->stream));
     CU(cudaMemsetAsync(d_seen, 0, (size_t)n_atoms * sizeof(unsigned long long), c->stream));
-    LAUNCH(c, BDR_K_SURFACE, k_surface_dist, blocks_for(edges, 128), 128, 0, c->labels[which], c->g,
-           c->list, edges, d_lat, d_atoms, d_best, d_seen, (int)n_atoms);
+    LAUNCH(c, BDR_K_SURFACE, k_surface_dist, blocks_for(c->list_n, 128), 128, 0, c->labels[which], c->g,
+           c->list, c->list_n, d_lat, d_atoms, d_best, d_seen, (int)n_atoms);
     CU(cudaMemcpyAsync(best.data(), d_best, (size_t)n_atoms * sizeof(double), cudaMemcpyDeviceToHost,
                        c->stream));
     CU(cudaMemcpyAsync(seen.data(), d_seen, (size_t)n_atoms * sizeof(unsigned long long),
@@ -1078,6 +1098,17 @@ int bdr_synth_general(bdr_ctx *c, int which, const double *lattice, const double
            d_sig, (int)n_atoms);
     CU(cudaStreamSynchronize(c->stream));
     cudaFree(d);
+    return 0;
+}
+
+int bdr_selftest_div(bdr_ctx *c, int64_t n, uint64_t seed, int64_t *mismatches) {
+    TRY(check(c));
+    TRY(zero_counter(c, CNT_ERROR));
+    LAUNCH(c, BDR_K_TRACE, k_selftest_div, blocks_for(n, 256), 256, 0, (unsigned long long)seed, n,
+           c->d_cnt + CNT_ERROR);
+    TRY(read_counters(c));
+    *mismatches = (int64_t)c->h_cnt[CNT_ERROR];
+    TRY(zero_counter(c, CNT_ERROR));
     return 0;
 }
 

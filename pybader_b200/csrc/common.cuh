@@ -97,8 +97,9 @@ struct bdr_ctx {
     double vac_tol = 0.0;
     bool verify_fixed_point = false;  // BDR_OPT_VERIFY_FIXED_POINT
     int8_t *known = nullptr;
-    uint8_t *tile_flag = nullptr;  // per edge-pass tile: holds an edge candidate
-    size_t tile_flag_n = 0;
+    uint32_t *ebits = nullptr;  // edge pass: 1 bit per voxel, nzw words per (x,y) row
+    uint32_t *vbits = nullptr;  // vacuum bits, same layout (second half of the ebits allocation)
+    int nzw = 0;
 
     int32_t *list = nullptr;   // work list (edge voxels to trace)
     int64_t list_cap = 0;

@@ -342,3 +342,16 @@ def test_properties_256(th, ut):
     assert hist[0][1] == 0
     np.testing.assert_array_equal(e.download_labels(LABELS_BADER, np.int32), lab_fp)
     e.close()
+
+
+def test_shared_reciprocal_division_is_ieee():
+    """the trace kernel's shared-reciprocal division == hardware fp64 division"""
+    import ctypes
+    from pybader_b200.engine import Engine
+    from pybader_b200._lib import check
+    e = Engine((4, 4, 4))
+    bad = ctypes.c_int64(-1)
+    for seed in (1, 2, 3):
+        check(e.lib.bdr_selftest_div(e.h, 1 << 24, seed, ctypes.byref(bad)))
+        assert bad.value == 0
+    e.close()
