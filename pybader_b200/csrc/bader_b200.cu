@@ -91,8 +91,10 @@ static int ensure_bits(bdr_ctx *c) {
     if (c->ebits) return 0;
     c->nzw = (c->g.nz + 31) / 32;
     const size_t words = (size_t)c->g.nx * c->g.ny * c->nzw;
-    CU(cudaMalloc((void **)&c->ebits, 2 * words * sizeof(uint32_t)));
+    CU(cudaMalloc((void **)&c->ebits, 4 * words * sizeof(uint32_t)));
     c->vbits = c->ebits + words;
+    c->cbits = c->vbits + words;
+    c->sbits = c->cbits + words;
     return 0;
 }
 static int ensure_rho(bdr_ctx *c, int which) {
@@ -210,7 +212,7 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
     if (n == 0) return 0;
     CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
     LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, code, c->N, c->minidx,
-           getenv("BDR_RESOLVE_MODE") ? atoi(getenv("BDR_RESOLVE_MODE")) : 0);
+           getenv("BDR_RESOLVE_MODE") ? atoi(getenv("BDR_RESOLVE_MODE")) : 3);
     std::vector<int32_t> order;
     TRY(rank_from_first(c, n, order, nullptr));
     std::vector<int32_t> roots((size_t)n);
@@ -252,20 +254,37 @@ static int renumber_dev(bdr_ctx *c, int which) {
 // ---------------------------------------------------------------------------
 // refinement pieces
 // ---------------------------------------------------------------------------
-static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges) {
+static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_changed = -1,
+                         int sticky_mode = 0) {
     TRY(ensure_known(c));
     TRY(ensure_bits(c));
     if (!c->labels[which]) return fail_msg("edge_find: label set is empty");
     TRY(ensure(&c->list, &c->list_cap, std::max<int64_t>(c->N / 16, 1024)));
     const dim3 grid((c->g.nz + 127) / 128, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
-    LAUNCH(c, BDR_K_EDGE_FLAG, k_edge_bits<EDGE_CX>, grid, 256, 0, c->labels[which], c->g, c->ebits,
-           c->vbits, c->nzw);
+    if ((c->g.nz & 3) == 0)
+        LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_bits<EDGE_CX, true>), grid, 256, 0, c->labels[which], c->g,
+               c->ebits, c->vbits, c->nzw);
+    else
+        LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_bits<EDGE_CX, false>), grid, 256, 0, c->labels[which], c->g,
+               c->ebits, c->vbits, c->nzw);
+    // masked pass (n_changed >= 0): list only the edges in the 27-neighbourhood
+    // of the voxels in c->list2 (the ones the last trace relabelled)
+    const uint32_t *mask = nullptr;
+    if (n_changed >= 0) {
+        const size_t words = (size_t)c->g.nx * c->g.ny * c->nzw;
+        CU(cudaMemsetAsync(c->cbits, 0, words * sizeof(uint32_t), c->stream));
+        if (n_changed > 0)
+            LAUNCH(c, BDR_K_EDGE_CHECK, k_bits_from_list, blocks_for(n_changed, 256), 256, 0, c->cbits,
+                   c->g, c->nzw, c->list2, n_changed);
+        mask = c->cbits;
+    }
     int64_t n = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_EDGES));
         LAUNCH(c, BDR_K_EDGE_DILATE, k_edge_known,
                dim3((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + 7) / 8), 256, 0, c->ebits, c->vbits,
-               c->known, c->g, c->nzw, c->d_cnt + CNT_EDGES, c->list, c->list_cap);
+               c->known, c->g, c->nzw, c->d_cnt + CNT_EDGES, c->list, c->list_cap, mask, c->sbits,
+               sticky_mode);
         TRY(read_counters(c));
         n = (int64_t)c->h_cnt[CNT_EDGES];
         if (n <= c->list_cap) break;
@@ -353,14 +372,16 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
     TRY(zero_counter(c, CNT_STEPS));
     TRY(zero_counter(c, CNT_ESCAPED));
     // list entries per warp: lanes refill from their warp's chunk, so longer chunks
-    // hide the spread of trajectory lengths; short lists keep every SM busy instead
-    int chunk = 32 * (int)std::min<int64_t>(16, std::max<int64_t>(1, n / (32 * 8192)));
+    // hide the spread of trajectory lengths, but the voxels in flight should stay a
+    // compact region that L2 can hold (measured best at 1024^3: 128); short lists
+    // keep every SM busy instead
+    int chunk = 32 * (int)std::min<int64_t>(4, std::max<int64_t>(1, n / (32 * 8192)));
     if (getenv("BDR_TRACE_CHUNK")) chunk = std::min(chunk, atoi(getenv("BDR_TRACE_CHUNK")));
     const int64_t n_warps = (n + chunk - 1) / chunk;
     LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
            rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c), W, T,
            c->list, n, chunk, (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
-           c->list2_cap, c->list3, c->list3_cap, step_cap);
+           c->list2_cap, c->list3, c->list3_cap, step_cap, c->use_term ? c->term : (int32_t *)nullptr);
     TRY(read_counters(c));
     if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
     const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
@@ -377,7 +398,8 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
                    rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
                    W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt,
                    want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
-                   (int32_t *)nullptr, (int64_t)0, step_cap);
+                   (int32_t *)nullptr, (int64_t)0, step_cap,
+                   c->use_term ? c->term : (int32_t *)nullptr);
         }
         TRY(read_counters(c));
         if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
@@ -476,26 +498,82 @@ static int refine_dev(bdr_ctx *c, int which, int mode, int64_t iters, const Weig
 // trajectory ends in").  One full edge pass + trace, then cheap incremental
 // rounds around the voxels that changed, then a full pass to confirm; repeat
 // until a full pass changes nothing.
+// drop queue entries whose cached trajectory end is still interior (c->list -> c->list)
+static int filter_cached_dev(bdr_ctx *c) {
+    const int64_t n = c->list_n;
+    if (n == 0) return 0;
+    TRY(ensure(&c->list3, &c->list3_cap, n));
+    TRY(zero_counter(c, CNT_CENTRES));
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_filter_cached, blocks_for(n, 256), 256, 0, c->list, n, c->term,
+           c->known, c->d_cnt + CNT_CENTRES, c->list3);
+    TRY(read_counters(c));
+    std::swap(c->list, c->list3);
+    std::swap(c->list_cap, c->list3_cap);
+    c->list_n = (int64_t)c->h_cnt[CNT_CENTRES];
+    return 0;
+}
+
+static int converge_rounds(bdr_ctx *c, int which, const Weights &W, const TGrad &T, bool dbg,
+                           int outer) {
+    int64_t edges = 0, changed = 0;
+    // conservative full pass: starts the sticky "never interior again" bits
+    TRY(edge_find_dev(c, which, &edges, -1, 1));
+    if (edges == 0) return 0;
+    CU(cudaMemsetAsync(c->term, 0xff, (size_t)c->N * sizeof(int32_t), c->stream));
+    TRY(trace_dev(c, which, W, T, &changed, true));
+    if (dbg) fprintf(stderr, "[bdr] full pass %d: edges %lld changed %lld\n", outer, (long long)edges,
+                     (long long)changed);
+    for (int inner = 0; inner < 4096 && changed > 0; ++inner) {
+        int64_t queued = 0;
+        if (changed * 2048 > c->N) {
+            // many voxels moved: a full (streaming) edge pass that lists only
+            // the edges next to them beats gathering their neighbourhoods
+            TRY(edge_find_dev(c, which, &queued, changed, 2));
+        } else {
+            TRY(incremental_dev(c, which, changed, &queued));
+        }
+        queued = c->list_n;
+        TRY(filter_cached_dev(c));
+        const int64_t kept = c->list_n;
+        TRY(trace_dev(c, which, W, T, &changed, true));
+        if (dbg) fprintf(stderr, "[bdr]   incremental %d: queued %lld traced %lld changed %lld\n", inner,
+                         (long long)queued, (long long)kept, (long long)changed);
+    }
+    return changed == 0 ? 0 : fail_msg("bader_calc(neargrid): incremental rounds did not settle");
+}
+
+// bader_calc('neargrid'): drive labels to the fixed point of the reference's
+// order-free refinement iteration ("every edge voxel carries the label its own
+// trajectory ends in").  One full edge pass + trace, then rounds around the
+// voxels that changed (a masked streaming pass while they are many, list-based
+// gathers when they are few).  Within these rounds the interior set only
+// shrinks, so a voxel whose recorded trajectory end is still interior is not
+// traced again.  With BDR_OPT_VERIFY_FIXED_POINT the whole thing repeats until
+// an exact full pass changes nothing.
 static int converge_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T) {
     const bool dbg = getenv("BDR_DEBUG") != nullptr;
-    const int max_outer = c->verify_fixed_point ? 64 : 1;
-    for (int outer = 0; outer < max_outer; ++outer) {
+    if (!c->term) CU(cudaMalloc((void **)&c->term, (size_t)c->N * sizeof(int32_t)));
+    TRY(ensure_known(c));
+    TRY(ensure_bits(c));
+    c->use_term = true;
+    int rc = converge_rounds(c, which, W, T, dbg, 0);
+    c->use_term = false;
+    if (rc || !c->verify_fixed_point) return rc;
+    for (int outer = 1; outer < 64; ++outer) {
+        // exact full pass (what the caller's refine() would run): if it moves
+        // nothing the labels are a fixed point of the reference iteration
         int64_t edges = 0, changed = 0;
         TRY(edge_find_dev(c, which, &edges));
         if (edges == 0) return 0;
         TRY(trace_dev(c, which, W, T, &changed, true));
-        if (dbg) fprintf(stderr, "[bdr] full pass %d: edges %lld changed %lld\n", outer,
+        if (dbg) fprintf(stderr, "[bdr] verify pass %d: edges %lld changed %lld\n", outer,
                          (long long)edges, (long long)changed);
         if (changed == 0) return 0;
-        for (int inner = 0; inner < 4096 && changed > 0; ++inner) {
-            int64_t queued = 0;
-            TRY(incremental_dev(c, which, changed, &queued));
-            TRY(trace_dev(c, which, W, T, &changed, true));
-            if (dbg) fprintf(stderr, "[bdr]   incremental %d: queued %lld changed %lld\n", inner,
-                             (long long)queued, (long long)changed);
-        }
+        c->use_term = true;
+        rc = converge_rounds(c, which, W, T, dbg, outer);
+        c->use_term = false;
+        if (rc) return rc;
     }
-    if (!c->verify_fixed_point) return 0;
     return fail_msg("bader_calc(neargrid): refinement did not reach a fixed point");
 }
 
@@ -625,7 +703,7 @@ int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *
     int64_t n = 0;
     TRY(stencil_dev(c, W, &n));
     LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, c->labels[BDR_LABELS_BADER],
-           c->N, (int32_t *)nullptr, 0);
+           c->N, (int32_t *)nullptr, 3);
     CU(cudaStreamSynchronize(c->stream));
     c->n_max = n;
     if (n_real) *n_real = n;
@@ -686,7 +764,7 @@ int bdr_destroy(bdr_ctx *c) {
         if (c->labels[i]) cudaFree(c->labels[i]);
     for (void *p : {(void *)c->known, (void *)c->list, (void *)c->list2, (void *)c->list3,
                     (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
-                    (void *)c->d_sums, c->stage, (void *)c->ebits})
+                    (void *)c->d_sums, c->stage, (void *)c->ebits, (void *)c->term})
         if (p) cudaFree(p);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->pinned) cudaFreeHost(c->pinned);

@@ -99,6 +99,10 @@ struct bdr_ctx {
     int8_t *known = nullptr;
     uint32_t *ebits = nullptr;  // edge pass: 1 bit per voxel, nzw words per (x,y) row
     uint32_t *vbits = nullptr;  // vacuum bits, same layout (second half of the ebits allocation)
+    uint32_t *cbits = nullptr;  // scratch bit volume (voxels relabelled by the last trace)
+    uint32_t *sbits = nullptr;  // sticky "was ever an edge or next to one" bits (conservative passes)
+    int32_t *term = nullptr;    // where each traced voxel's trajectory ended (bader_calc('neargrid') only)
+    bool use_term = false;
     int nzw = 0;
 
     int32_t *list = nullptr;   // work list (edge voxels to trace)
