@@ -196,6 +196,16 @@ int bdr_edge_pass(bdr_ctx *ctx, int which, int64_t *edges);
 int bdr_trace_pass(bdr_ctx *ctx, int which, const double *dist_mat, const double *T_grad,
                    int64_t *changed, int64_t *escaped);
 
+/* Trajectories that leave a rank's window continue on the owning rank's memory
+ * (CUDA IPC mappings over NVLink / NVSwitch) instead of needing deep halos:
+ * export writes three 64-byte IPC handles (density, labels, known); attach
+ * receives all ranks' handles (world * 3 * 64 bytes, rank major), the global
+ * slab bounds (world + 1 first planes) and the global nx.  Every rank must have
+ * finished its edge pass before any rank starts a trace pass.              */
+int bdr_slab_ipc_export(bdr_ctx *ctx, void *handles);
+int bdr_slab_ipc_attach(bdr_ctx *ctx, int world, int rank, const void *all_handles,
+                        const int64_t *bounds, int64_t nx_global);
+
 /* ---- options ------------------------------------------------------------- */
 /* BDR_OPT_VERIFY_FIXED_POINT (default 0): bader_calc('neargrid') drives the
  * labels to quiescence with one full edge pass plus incremental rounds; with

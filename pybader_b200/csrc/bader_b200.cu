@@ -378,10 +378,17 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
     int chunk = 32 * (int)std::min<int64_t>(4, std::max<int64_t>(1, n / (32 * 8192)));
     if (getenv("BDR_TRACE_CHUNK")) chunk = std::min(chunk, atoi(getenv("BDR_TRACE_CHUNK")));
     const int64_t n_warps = (n + chunk - 1) / chunk;
-    LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
-           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c), W, T,
-           c->list, n, chunk, (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
-           c->list2_cap, c->list3, c->list3_cap, step_cap, c->use_term ? c->term : (int32_t *)nullptr);
+    const PeerView *pv = static_cast<const PeerView *>(c->peer_view);
+    if (pv)
+        LAUNCH(c, BDR_K_TRACE, (k_trace_peer<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
+               *pv, c->labels[which], c->known, c->g, window_of(c), W, T, c->list, n, chunk,
+               (long long *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
+               c->list2_cap, c->list3, c->list3_cap, step_cap);
+    else
+        LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
+               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c), W, T,
+               c->list, n, chunk, (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
+               c->list2_cap, c->list3, c->list3_cap, step_cap, c->use_term ? c->term : (int32_t *)nullptr);
     TRY(read_counters(c));
     if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
     const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
@@ -390,17 +397,24 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
         // in batches so the scratch stays bounded (SLOW_CAP * 4 B per voxel)
         constexpr int SLOW_CAP = 4096;
         const int64_t batch = 16384;
-        TRY(ensure_stage(c, (size_t)std::min(ov, batch) * SLOW_CAP * sizeof(int32_t)));
+        TRY(ensure_stage(c, (size_t)(std::min(ov, batch) + 128) * SLOW_CAP * sizeof(long long)));
         CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
         for (int64_t o = 0; o < ov; o += batch) {
             const int64_t m = std::min(batch, ov - o);
-            LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
-                   rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
-                   W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt,
-                   want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
-                   (int32_t *)nullptr, (int64_t)0, step_cap,
-                   c->use_term ? c->term : (int32_t *)nullptr);
-        }
+            if (pv)
+                LAUNCH(c, BDR_K_TRACE, (k_trace_peer<SLOW_CAP, true>), blocks_for(m, 128), 128, 0, *pv,
+                       c->labels[which], c->known, c->g, window_of(c), W, T, c->list3 + o, m, 32,
+                       (long long *)c->stage, c->d_cnt,
+                       want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
+                       (int32_t *)nullptr, (int64_t)0, step_cap);
+            else
+                LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
+                       rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
+                       W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt,
+                       want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
+                       (int32_t *)nullptr, (int64_t)0, step_cap,
+                       c->use_term ? c->term : (int32_t *)nullptr);
+            }
         TRY(read_counters(c));
         if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
     }
@@ -692,6 +706,61 @@ int bdr_slab_create(int device, int64_t nx_window, int64_t ny, int64_t nz, int h
     c->halo = halo;
     c->own_lo = (int64_t)halo * ny * nz;
     c->own_hi = (nx_window - halo) * ny * nz;
+    // the arrays other ranks map (bdr_slab_ipc_export) exist from the start
+    TRY(ensure_rho(c, BDR_RHO_REFERENCE));
+    TRY(ensure_labels(c, BDR_LABELS_BADER));
+    TRY(ensure_known(c));
+    CU(cudaMemsetAsync(c->known, 0, (size_t)c->N, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_slab_ipc_export(bdr_ctx *c, void *handles) {
+    TRY(check(c));
+    if (c->halo == 0) return fail_msg("bdr_slab_ipc_export: not a slab handle");
+    cudaIpcMemHandle_t *h = static_cast<cudaIpcMemHandle_t *>(handles);
+    CU(cudaIpcGetMemHandle(&h[0], c->rho[BDR_RHO_REFERENCE]));
+    CU(cudaIpcGetMemHandle(&h[1], c->labels[BDR_LABELS_BADER]));
+    CU(cudaIpcGetMemHandle(&h[2], c->known));
+    return 0;
+}
+
+int bdr_slab_ipc_attach(bdr_ctx *c, int world, int rank, const void *all_handles,
+                        const int64_t *bounds, int64_t nx_global) {
+    TRY(check(c));
+    if (c->halo == 0) return fail_msg("bdr_slab_ipc_attach: not a slab handle");
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world)
+        return fail_msg("bdr_slab_ipc_attach: bad world / rank");
+    PeerView *pv = new PeerView();
+    memset(pv, 0, sizeof *pv);
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            pv->rho[r] = c->rho[BDR_RHO_REFERENCE];
+            pv->lab[r] = c->labels[BDR_LABELS_BADER];
+            pv->known[r] = c->known;
+            continue;
+        }
+        void *p[3];
+        for (int k = 0; k < 3; ++k) {
+            cudaIpcMemHandle_t hk = h[r * 3 + k];
+            CU(cudaIpcOpenMemHandle(&p[k], hk, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(p[k]);
+        }
+        pv->rho[r] = static_cast<const double *>(p[0]);
+        pv->lab[r] = static_cast<const int32_t *>(p[1]);
+        pv->known[r] = static_cast<const int8_t *>(p[2]);
+    }
+    for (int r = 0; r <= world; ++r) pv->bound[r] = (int)bounds[r];
+    pv->world = world;
+    pv->rank = rank;
+    pv->halo = c->halo;
+    pv->NX = (int)nx_global;
+    pv->x0w = (int)bounds[rank] - c->halo;
+    pv->W = c->g.nx;
+    if (bounds[rank + 1] - bounds[rank] + 2 * c->halo != c->g.nx)
+        return fail_msg("bdr_slab_ipc_attach: slab bounds do not match the window");
+    c->peer_view = pv;
     return 0;
 }
 
@@ -772,6 +841,8 @@ int bdr_destroy(bdr_ctx *c) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    delete static_cast<PeerView *>(c->peer_view);
     for (auto e : c->pool) cudaEventDestroy(e);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);

@@ -130,6 +130,10 @@ struct bdr_ctx {
     void *pinned = nullptr;  // pinned host bounce buffer
     size_t pinned_bytes = 0;
 
+    // sharded runs: device pointers of every rank's arrays (CUDA IPC), see kernels.cuh K4p
+    void *peer_view = nullptr;      // bdr::PeerView, host copy
+    std::vector<void *> ipc_opened;  // pointers to close on destroy
+
     bool prof = false;
     std::vector<bdr::ProfRec> recs;
     std::vector<cudaEvent_t> pool;

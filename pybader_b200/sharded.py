@@ -23,6 +23,8 @@ The protocol code below only touches plane- and root-sized tensors and is
 device agnostic, so tests drive it on CPU over gloo with a model backend.
 """
 import ctypes
+import os
+import sys
 
 import numpy as np
 import torch
@@ -107,6 +109,23 @@ class ShardedBader:
         self.window_x = (np.arange(self.W) + self.x0 - self.halo) % nx
         self.backend = backend_factory((self.W, self.ny, self.nz), self.halo)
         self.maxima = np.zeros((0, 3), dtype=np.int64)
+        self.bounds = b
+        # trajectories that leave this rank's window continue on the owner's
+        # memory (CUDA IPC over NVLink); the CPU model backend has no such need
+        if hasattr(self.backend, 'ipc_export'):
+            self._attach_peers()
+
+    def _attach_peers(self):
+        be = self.backend
+        mine = torch.frombuffer(bytearray(be.ipc_export()), dtype=torch.uint8).to(be.device)
+        if self.comm.world > 1:
+            allh = [torch.empty_like(mine) for _ in range(self.comm.world)]
+            dist.all_gather(allh, mine, group=self.comm.group)
+            allh = torch.cat(allh)
+        else:
+            allh = mine
+        be.ipc_attach(self.comm.world, self.comm.rank, bytes(allh.cpu().numpy().tobytes()),
+                      self.bounds, self.shape[0])
 
     # ---- helpers -----------------------------------------------------------
     def _gid_of_window_index(self, widx):
@@ -128,9 +147,15 @@ class ShardedBader:
         t[self.W - H:].copy_(hi)
 
     # ---- ongrid: seed, exits, numbering -----------------------------------
+    def _dbg(self, msg):
+        if os.environ.get('BDR_DEBUG'):
+            print(f"[sharded r{self.comm.rank}] {msg}", file=sys.stderr, flush=True)
+
     def ongrid(self, dist_mat):
         be, H, P = self.backend, self.halo, self.plane
+        self._dbg("seed")
         n_real, exit_base = be.seed(dist_mat)
+        self._dbg(f"seeded: {n_real} local maxima")
         codes = be.labels()                      # int32 [W, ny, nz]: -1 vacuum, -2-s slots
         dev = codes.device
         n_slots = exit_base + n_real
@@ -147,14 +172,22 @@ class ShardedBader:
             out[sel] = G[s[sel]]
             return out
 
-        for _ in range(self.comm.world + 1):
+        # one round per slab boundary an ascent path crosses (paths are acyclic, so
+        # this ends; a path winding along a boundary can need more than `world`)
+        self.exit_rounds = 0
+        for _ in range(64 + 2 * self.comm.world):
+            self.exit_rounds += 1
             up, down = export(self.nxl), export(2 * H - 1)
             lo, hi = torch.empty_like(up), torch.empty_like(down)
             self.comm.ring_exchange(up, down, lo, hi)
             G[:P] = lo
             G[P:2 * P] = hi
             pending = int(((up == UNRESOLVED).sum() + (down == UNRESOLVED).sum()).item())
-            if self.comm.allreduce_sum(pending, dev) == 0:
+            pending = self.comm.allreduce_sum(pending, dev)
+            if os.environ.get('BDR_DEBUG') and self.comm.rank == 0:
+                print(f"[sharded] exit round {self.exit_rounds}: pending {pending}", file=sys.stderr,
+                      flush=True)
+            if pending == 0:
                 break
         else:
             raise RuntimeError("exit resolution did not converge")
@@ -162,6 +195,7 @@ class ShardedBader:
         # because every plane a neighbour needs from me was exported resolved
 
         # first owned voxel of every slot -> per root id
+        self._dbg("numbering")
         first_w = be.first_voxel(n_slots).to(torch.int64)          # window-linear or NO_VOXEL
         used = first_w != NO_VOXEL
         if bool((G[used] == UNRESOLVED).any()):
@@ -189,7 +223,9 @@ class ShardedBader:
             hit = uniq[pos] == G[ok]
             vals = torch.where(hit, number_of[pos], torch.full_like(pos, -1)).to(torch.int32)
             rank_lut[ok] = vals
+        self._dbg("apply rank")
         be.apply_rank(rank_lut)
+        self._dbg("ongrid done")
         mg = uniq[order].cpu().numpy()
         self.maxima = np.stack([mg // P, (mg // self.nz) % self.ny, mg % self.nz], axis=1)
         return self.maxima
@@ -201,24 +237,33 @@ class ShardedBader:
         be, dev = self.backend, self.backend.labels().device
         history = []
         it = 0
+        dbg = os.environ.get('BDR_DEBUG') and self.comm.rank == 0
         while iters < 0 or it < iters:
             self.exchange_halo(be.labels())
             edges = be.edge_pass()
+            # every rank's classification must be complete before any rank's
+            # trajectories may read it (remote reads in the trace kernel)
+            edges = self.comm.allreduce_sum(edges, dev)
             changed, escaped = be.trace_pass(dist_mat, T_grad)
             if self.comm.allreduce_sum(escaped, dev):
                 raise RuntimeError("a trajectory left the slab halo: raise `halo`")
-            edges = self.comm.allreduce_sum(edges, dev)
             changed = self.comm.allreduce_sum(changed, dev)
             history.append((edges, changed))
+            if dbg:
+                print(f"[sharded] pass {it}: edges {edges} changed {changed}", file=sys.stderr, flush=True)
             it += 1
             if changed == 0 or edges == 0:
                 break
         self.exchange_halo(be.labels())
         return history
 
-    def neargrid(self, dist_mat, T_grad):
+    def neargrid(self, dist_mat, T_grad, max_passes=64):
+        """ongrid seed, then full Jacobi passes until nothing changes (at most
+        `max_passes`; `self.settled` says whether the last one was quiet)"""
         self.ongrid(dist_mat)
-        self.refine(dist_mat, T_grad, -1)
+        hist = self.refine(dist_mat, T_grad, max_passes)
+        self.settled = bool(hist) and (hist[-1][1] == 0 or hist[-1][0] == 0) or not hist
+        self.neargrid_history = hist
         return self.maxima
 
     def charge_sum(self, n, voxel_volume, which_density=0):
@@ -269,6 +314,16 @@ class SlabBackend:
             self.lib.bdr_destroy(self.h)
             self.h = None
 
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(3 * 64)
+        self.check(self.lib.bdr_slab_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_attach(self, world, rank, all_handles, bounds, nx_global):
+        b = np.ascontiguousarray(bounds, dtype=np.int64)
+        self.check(self.lib.bdr_slab_ipc_attach(self.h, int(world), int(rank), all_handles,
+                                                b.ctypes.data, int(nx_global)))
+
     def _ptr(self, what):
         p = ctypes.c_void_p()
         self.check(self.lib.bdr_device_ptr(self.h, what, ctypes.byref(p)))
@@ -292,11 +347,19 @@ class SlabBackend:
         self.check(self.lib.bdr_synth_separable(self.h, which, tx.ctypes.data, ty.ctypes.data,
                                                 tz.ctypes.data, tx.shape[0]))
 
+    def _sync(self):
+        """torch works on its own stream, the library on the handle's: order them
+        (a late halo copy into the label array must not land on fresh codes)"""
+        torch.cuda.synchronize(self.device)
+
     def clear_labels(self):
+        self._sync()
         self.check(self.lib.bdr_clear_labels(self.h, 0))
+        self.check(self.lib.bdr_synchronize(self.h))
         self._labels = None
 
     def vacuum_assign(self, tol, dV):
+        self._sync()
         q, v = ctypes.c_double(0), ctypes.c_double(0)
         self.check(self.lib.bdr_vacuum_assign(self.h, float(tol), float(dV), 0, ctypes.byref(q),
                                               ctypes.byref(v)))
@@ -309,6 +372,7 @@ class SlabBackend:
         return self._labels
 
     def seed(self, dist_mat):
+        self._sync()
         d = np.ascontiguousarray(dist_mat, dtype=np.float64)
         n, xb = ctypes.c_int64(0), ctypes.c_int64(0)
         self.check(self.lib.bdr_slab_seed(self.h, d.ctypes.data, ctypes.byref(n), ctypes.byref(xb)))
@@ -322,6 +386,7 @@ class SlabBackend:
 
     def first_voxel(self, n_slots):
         out = torch.empty(max(n_slots, 1), dtype=torch.int32, device=self.device)
+        self._sync()
         self.check(self.lib.bdr_slab_first_voxel(self.h, int(n_slots), out.data_ptr()))
         return out[:n_slots]
 
@@ -337,6 +402,7 @@ class SlabBackend:
         return e.value
 
     def trace_pass(self, dist_mat, T_grad):
+        self._sync()
         d = np.ascontiguousarray(dist_mat, dtype=np.float64)
         t = np.ascontiguousarray(T_grad, dtype=np.float64)
         ch, esc = ctypes.c_int64(0), ctypes.c_int64(0)
@@ -346,6 +412,7 @@ class SlabBackend:
 
     def charge_sum(self, n, dV, which_density=0):
         q, v = np.zeros(n), np.zeros(n)
+        self._sync()
         self.check(self.lib.bdr_charge_sum(self.h, 0, which_density, float(dV), n, q.ctypes.data,
                                            v.ctypes.data))
         return q, v
@@ -427,6 +494,8 @@ def bench(args, rank, world, local):
             "roofline": None, "cpu_baseline": None,
             "e2e": None, "gpu_launches": launches, "clocks": clocks.stop(),
             "wall_ms_per_step": wall / args.steps, "refine_history_last_step": hist,
+            "exit_rounds": sb.exit_rounds, "neargrid_passes": len(sb.neargrid_history),
+            "neargrid_settled": sb.settled,
         }
         print(json.dumps(out))
     dist.destroy_process_group()
