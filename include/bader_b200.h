@@ -196,6 +196,19 @@ int bdr_edge_pass(bdr_ctx *ctx, int which, int64_t *edges);
 int bdr_trace_pass(bdr_ctx *ctx, int which, const double *dist_mat, const double *T_grad,
                    int64_t *changed, int64_t *escaped);
 
+/* bader_calc('neargrid') of a sharded run, cut where the ranks have to meet:
+ * first_pass = full edge classification (starts the conservative interior
+ * bits); trace = one Jacobi trace of the queued voxels (want_list keeps the
+ * relabelled voxels for the next requeue); requeue = queue the edges next to
+ * the voxels relabelled by the last trace plus `dev_extra` (window-linear
+ * indices of halo voxels a neighbour relabelled), a masked streaming pass when
+ * they are many, list-based gathers when they are few.                      */
+int bdr_slab_first_pass(bdr_ctx *ctx, int which, int64_t *edges);
+int bdr_slab_trace(bdr_ctx *ctx, int which, const double *dist_mat, const double *T_grad,
+                   int want_list, int64_t *changed);
+int bdr_slab_requeue(bdr_ctx *ctx, int which, const int32_t *dev_extra, int64_t n_extra,
+                     int64_t *queued);
+
 /* Trajectories that leave a rank's window continue on the owning rank's memory
  * (CUDA IPC mappings over NVLink / NVSwitch) instead of needing deep halos:
  * export writes three 64-byte IPC handles (density, labels, known); attach

@@ -808,6 +808,69 @@ int bdr_slab_roots(bdr_ctx *c, int32_t *host_out, int64_t cap) {
 
 int bdr_edge_pass(bdr_ctx *c, int which, int64_t *edges) { return bdr_edge_find(c, which, edges); }
 
+// sharded bader_calc('neargrid'): the same conservative rounds as converge_dev,
+// cut where the ranks have to meet (sharded.py drives them)
+int bdr_slab_first_pass(bdr_ctx *c, int which, int64_t *edges) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_slab_first_pass: bad label set");
+    int64_t e = 0;
+    TRY(edge_find_dev(c, which, &e, -1, 1));
+    c->last_changed = 0;
+    CU(cudaStreamSynchronize(c->stream));
+    if (edges) *edges = e;
+    return 0;
+}
+
+int bdr_slab_trace(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
+                   int want_list, int64_t *changed) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_slab_trace: bad label set");
+    if (!c->known) return fail_msg("bdr_slab_trace: no edge pass has run");
+    const Weights W = make_weights(dist_mat);
+    const TGrad T = make_tgrad(T_grad);
+    int64_t ch = 0;
+    TRY(trace_dev(c, which, W, T, &ch, want_list != 0));
+    c->last_changed = want_list ? ch : 0;
+    CU(cudaStreamSynchronize(c->stream));
+    if (changed) *changed = ch;
+    return 0;
+}
+
+int bdr_slab_requeue(bdr_ctx *c, int which, const int32_t *dev_extra, int64_t n_extra,
+                     int64_t *queued) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_slab_requeue: bad label set");
+    const int64_t n = c->last_changed + n_extra;
+    if (n_extra > 0) {
+        // voxels a neighbour relabelled on the planes next to this slab count
+        // as changed here too: their 27-neighbourhoods reach owned voxels
+        if (c->last_changed + n_extra > c->list2_cap) {
+            int32_t *grown = nullptr;
+            const int64_t cap = n + n / 4 + 1024;
+            CU(cudaMalloc((void **)&grown, (size_t)cap * sizeof(int32_t)));
+            if (c->last_changed)
+                CU(cudaMemcpyAsync(grown, c->list2, (size_t)c->last_changed * sizeof(int32_t),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->list2) cudaFree(c->list2);
+            c->list2 = grown;
+            c->list2_cap = cap;
+        }
+        CU(cudaMemcpyAsync(c->list2 + c->last_changed, dev_extra, (size_t)n_extra * sizeof(int32_t),
+                           cudaMemcpyDeviceToDevice, c->stream));
+    }
+    int64_t q = 0;
+    if (n * 2048 > c->N) {
+        TRY(edge_find_dev(c, which, &q, n, 2));
+    } else {
+        TRY(incremental_dev(c, which, n, &q));
+    }
+    q = c->list_n;
+    CU(cudaStreamSynchronize(c->stream));
+    if (queued) *queued = q;
+    return 0;
+}
+
 int bdr_trace_pass(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
                    int64_t *changed, int64_t *escaped) {
     TRY(check(c));

@@ -103,6 +103,7 @@ struct bdr_ctx {
     uint32_t *sbits = nullptr;  // sticky "was ever an edge or next to one" bits (conservative passes)
     int32_t *term = nullptr;    // where each traced voxel's trajectory ended (bader_calc('neargrid') only)
     bool use_term = false;
+    int64_t last_changed = 0;   // entries of list2 written by the last trace (slab rounds)
     int nzw = 0;
 
     int32_t *list = nullptr;   // work list (edge voxels to trace)

@@ -258,11 +258,37 @@ class ShardedBader:
         return history
 
     def neargrid(self, dist_mat, T_grad, max_passes=64):
-        """ongrid seed, then full Jacobi passes until nothing changes (at most
-        `max_passes`; `self.settled` says whether the last one was quiet)"""
+        """ongrid seed, then Jacobi rounds until nothing changes (at most
+        `max_passes`; `self.settled` says whether the last one was quiet).
+        A backend with `requeue` re-traces only the edges next to voxels that
+        moved (like the single-GPU bader_calc); otherwise full passes."""
         self.ongrid(dist_mat)
-        hist = self.refine(dist_mat, T_grad, max_passes)
-        self.settled = bool(hist) and (hist[-1][1] == 0 or hist[-1][0] == 0) or not hist
+        be = self.backend
+        if not hasattr(be, 'requeue'):
+            hist = self.refine(dist_mat, T_grad, max_passes)
+            self.settled = not hist or hist[-1][1] == 0 or hist[-1][0] == 0
+            self.neargrid_history = hist
+            return self.maxima
+        dev, H, P = be.labels().device, self.halo, self.plane
+        lab = be.labels()
+        self.exchange_halo(lab)
+        edges = self.comm.allreduce_sum(be.first_pass(), dev)      # also the barrier before remote reads
+        changed = self.comm.allreduce_sum(be.trace(dist_mat, T_grad, True), dev) if edges else 0
+        hist = [(edges, changed)]
+        self._dbg(f"first pass: edges {edges} changed {changed}")
+        while changed > 0 and len(hist) < max_passes:
+            # the planes next to the owned slab, before and after the exchange
+            old_lo, old_hi = lab[H - 1].clone(), lab[self.W - H].clone()
+            self.exchange_halo(lab)
+            lo = torch.nonzero((lab[H - 1] != old_lo).reshape(-1)).reshape(-1) + (H - 1) * P
+            hi = torch.nonzero((lab[self.W - H] != old_hi).reshape(-1)).reshape(-1) + (self.W - H) * P
+            extra = torch.cat([lo, hi]).to(torch.int32)
+            queued = self.comm.allreduce_sum(be.requeue(extra), dev)
+            changed = self.comm.allreduce_sum(be.trace(dist_mat, T_grad, True), dev)
+            hist.append((queued, changed))
+            self._dbg(f"round {len(hist) - 1}: queued {queued} changed {changed}")
+        self.exchange_halo(lab)
+        self.settled = changed == 0
         self.neargrid_history = hist
         return self.maxima
 
@@ -401,6 +427,29 @@ class SlabBackend:
         self.check(self.lib.bdr_edge_pass(self.h, 0, ctypes.byref(e)))
         return e.value
 
+    def first_pass(self):
+        self._sync()
+        e = ctypes.c_int64(0)
+        self.check(self.lib.bdr_slab_first_pass(self.h, 0, ctypes.byref(e)))
+        return e.value
+
+    def trace(self, dist_mat, T_grad, want_list):
+        self._sync()
+        d = np.ascontiguousarray(dist_mat, dtype=np.float64)
+        t = np.ascontiguousarray(T_grad, dtype=np.float64)
+        ch = ctypes.c_int64(0)
+        self.check(self.lib.bdr_slab_trace(self.h, 0, d.ctypes.data, t.ctypes.data, int(want_list),
+                                           ctypes.byref(ch)))
+        return ch.value
+
+    def requeue(self, extra):
+        extra = extra.contiguous()
+        self._sync()
+        q = ctypes.c_int64(0)
+        self.check(self.lib.bdr_slab_requeue(self.h, 0, extra.data_ptr() if extra.numel() else None,
+                                             int(extra.numel()), ctypes.byref(q)))
+        return q.value
+
     def trace_pass(self, dist_mat, T_grad):
         self._sync()
         d = np.ascontiguousarray(dist_mat, dtype=np.float64)
@@ -457,7 +506,7 @@ def bench(args, rank, world, local):
 
     def step():
         sb.backend.clear_labels()
-        sb.neargrid(dm, T)                 # ongrid seed + exits + numbering + passes to quiescence
+        sb.neargrid(dm, T)                 # ongrid seed + exits + numbering + rounds to quiescence
         return sb.refine(dm, T, 2)         # the caller's refine(): full pass(es)
 
     for _ in range(args.warmup):

@@ -49,8 +49,16 @@ def _worker(rank, world, port, out):
         hist = sb.refine(dm, T, -1)
         lab_ng = sb.owned_labels().cpu().numpy().copy()
         q, v = sb.charge_sum(mx.shape[0], dV)
+        # bader_calc('neargrid') of the sharded path: incremental rounds, then one exact pass
+        sb.backend.clear_labels()
+        mx2 = sb.neargrid(dm, T)
+        assert sb.settled
+        hist2 = sb.refine(dm, T, 1)
+        lab_nn = sb.owned_labels().cpu().numpy().copy()
+        q2, v2 = sb.charge_sum(mx2.shape[0], dV)
         np.savez(os.path.join(out, f'r{rank}.npz'), maxima=mx, lab_on=lab_on, lab_ng=lab_ng,
-                 hist=np.array(hist), q=q, v=v)
+                 hist=np.array(hist), q=q, v=v, maxima2=mx2, lab_nn=lab_nn, hist2=np.array(hist2),
+                 q2=q2, v2=v2)
     finally:
         dist.destroy_process_group()
 
@@ -74,6 +82,12 @@ def test_two_gpu_labels_equal_single_gpu(tmp_path):
     ref_ng = e.download_labels(LABELS_BADER, np.int32)
     q, v = np.zeros(mx.shape[0]), np.zeros(mx.shape[0])
     e.charge_sum(LABELS_BADER, 0, dV, q, v)
+    e.clear_labels()
+    mxn = e.bader_calc('neargrid', dm, T)
+    e.refine(LABELS_BADER, 'all', 1, dm, T)
+    ref_nn = e.download_labels(LABELS_BADER, np.int32)
+    qn, vn = np.zeros(mxn.shape[0]), np.zeros(mxn.shape[0])
+    e.charge_sum(LABELS_BADER, 0, dV, qn, vn)
     e.close()
     parts = [np.load(os.path.join(str(tmp_path), f'r{r}.npz')) for r in range(2)]
     np.testing.assert_array_equal(parts[0]['maxima'], mx)
@@ -82,3 +96,11 @@ def test_two_gpu_labels_equal_single_gpu(tmp_path):
     assert [tuple(h) for h in parts[0]['hist']] == hist
     np.testing.assert_allclose(parts[0]['q'], q, rtol=1e-12)
     np.testing.assert_allclose(parts[0]['v'], v, rtol=1e-12)
+    # sharded bader_calc('neargrid') + one exact pass vs the single-GPU one: same
+    # maxima, the exact pass finds (next to) nothing to do, labels >= 99.9 % equal
+    np.testing.assert_array_equal(parts[0]['maxima2'], mxn)
+    assert int(parts[0]['hist2'][0][1]) <= max(2, 1e-4 * ref_nn.size)
+    lab_nn = np.concatenate([p['lab_nn'] for p in parts])
+    assert np.mean(lab_nn == ref_nn) >= 0.999
+    np.testing.assert_allclose(parts[0]['q2'], qn, rtol=1e-6)
+    np.testing.assert_allclose(parts[0]['v2'], vn, rtol=1e-6)
