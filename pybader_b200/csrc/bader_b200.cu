@@ -163,33 +163,38 @@ static int rank_from_first(bdr_ctx *c, int64_t n, std::vector<int32_t> &order, b
 // real maxima follow
 static int exit_base_of(const bdr_ctx *c) { return c->halo > 0 ? 2 * c->g.ny * c->g.nz : 0; }
 
-static int stencil_dev(bdr_ctx *c, const Weights &W_full, int64_t *n_real) {
-    TRY(ensure_labels(c, BDR_LABELS_BADER));
-    TRY(ensure_slots(c, 4096));
+// the stencil pass over planes [x_begin, x_end) (x_begin a multiple of SX)
+static int stencil_launch(bdr_ctx *c, const HalfWeights &W, int x_begin, int x_end) {
     const size_t smem = stencil_smem();
     int32_t *code = c->labels[BDR_LABELS_BADER];
     const double *rho = rho_ptr(c, BDR_RHO_REFERENCE);
+    const int xb = exit_base_of(c);
+    dim3 grid = tile_grid(c->g, SX);
+    grid.z = (x_end - x_begin + SX - 1) / SX;
+    // vacuum comes from the fused tolerance test when the labels were made
+    // by bdr_vacuum_assign / bdr_clear_labels on this handle, else from
+    // the label array itself (-1 entries)
+    if (c->vac_mode == VAC_NONE)
+        LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_NONE>), grid, 256, smem, rho, code,
+               c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin);
+    else if (c->vac_mode == VAC_TOL)
+        LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_TOL>), grid, 256, smem, rho, code,
+               c->g, W, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin);
+    else
+        LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>), grid, 256, smem, rho,
+               code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin);
+    return 0;
+}
+
+static int stencil_dev(bdr_ctx *c, const Weights &W_full, int64_t *n_real) {
+    TRY(ensure_labels(c, BDR_LABELS_BADER));
+    TRY(ensure_slots(c, 4096));
     if (!weights_symmetric(W_full))
         return fail_msg("bader_calc: dist_mat[-d] != dist_mat[d]; not a step-length table");
     const HalfWeights W = half_weights(W_full);
-    const int xb = exit_base_of(c);
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_ROOTS));
-        // vacuum comes from the fused tolerance test when the labels were made
-        // by bdr_vacuum_assign / bdr_clear_labels on this handle, else from
-        // the label array itself (-1 entries)
-        if (c->vac_mode == VAC_NONE)
-            LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_NONE>), tile_grid(c->g, SX),
-                   256, smem, rho, code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap,
-                   xb);
-        else if (c->vac_mode == VAC_TOL)
-            LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_TOL>), tile_grid(c->g, SX),
-                   256, smem, rho, code, c->g, W, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots,
-                   c->slots_cap, xb);
-        else
-            LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>),
-                   tile_grid(c->g, SX), 256, smem, rho, code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS,
-                   c->roots, c->slots_cap, xb);
+        TRY(stencil_launch(c, W, 0, c->g.nx));
         TRY(read_counters(c));
         const int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
         if (n <= c->slots_cap) break;
@@ -202,10 +207,58 @@ static int stencil_dev(bdr_ctx *c, const Weights &W_full, int64_t *n_real) {
     return 0;
 }
 
-static int ongrid_dev(bdr_ctx *c, const Weights &W_full) {
+// bdr_run: the density arrives in x chunks on a copy stream and the stencil
+// pass follows it chunk by chunk on the compute stream, so the first kernel of
+// the pipeline hides under the PCIe transfer (which is ~2.5x longer than all
+// kernels together at 1024^3).  A chunk's stencil needs one plane of the next
+// chunk, and chunk 0 needs the last plane (periodic), so it runs last.
+static int upload_and_stencil_dev(bdr_ctx *c, const double *host, const Weights &W_full,
+                                  int64_t *n_real) {
+    TRY(ensure_rho(c, BDR_RHO_REFERENCE));
+    TRY(ensure_labels(c, BDR_LABELS_BADER));
+    TRY(ensure_slots(c, 4096));
+    if (!weights_symmetric(W_full))
+        return fail_msg("bader_calc: dist_mat[-d] != dist_mat[d]; not a step-length table");
+    const HalfWeights W = half_weights(W_full);
+    const int CH = 4 * SX;
+    const int nchunks = (c->g.nx + CH - 1) / CH;
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    while ((int)c->chunk_events.size() < nchunks) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_events.push_back(e);
+    }
+    const int64_t plane = (int64_t)c->g.ny * c->g.nz;
+    double *rho = c->rho[BDR_RHO_REFERENCE];
+    CU(cudaStreamSynchronize(c->stream));  // nothing may still read the old density
+    for (int i = 0; i < nchunks; ++i) {
+        const int xa = i * CH, xe = std::min(c->g.nx, xa + CH);
+        CU(cudaMemcpyAsync(rho + xa * plane, host + xa * plane, (size_t)(xe - xa) * plane * sizeof(double),
+                           cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->chunk_events[(size_t)i], c->copy_stream));
+    }
+    TRY(zero_counter(c, CNT_ROOTS));
+    for (int i = 1; i < nchunks; ++i) {
+        const int xa = i * CH, xe = std::min(c->g.nx, xa + CH);
+        CU(cudaStreamWaitEvent(c->stream, c->chunk_events[(size_t)std::min(i + 1, nchunks - 1)], 0));
+        TRY(stencil_launch(c, W, xa, xe));
+    }
+    CU(cudaStreamWaitEvent(c->stream, c->chunk_events[(size_t)nchunks - 1], 0));
+    TRY(stencil_launch(c, W, 0, std::min(c->g.nx, CH)));
+    TRY(read_counters(c));
+    int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
+    if (n > c->slots_cap) {  // more maxima than slots: redo on the resident density
+        TRY(ensure_slots(c, n));
+        TRY(stencil_dev(c, W_full, &n));
+    }
+    *n_real = n;
+    return 0;
+}
+
+static int ongrid_dev(bdr_ctx *c, const Weights &W_full, int64_t seeded = -1) {
     if (c->halo > 0) return fail_msg("bader_calc: slab windows are driven through the bdr_slab_* entry points");
-    int64_t n = 0;
-    TRY(stencil_dev(c, W_full, &n));
+    int64_t n = seeded;  // >= 0: the stencil pass already ran (bdr_run's pipelined upload)
+    if (n < 0) TRY(stencil_dev(c, W_full, &n));
     int32_t *code = c->labels[BDR_LABELS_BADER];
     c->n_max = n;
     c->maxima.assign((size_t)n * 3, 0);
@@ -909,6 +962,8 @@ int bdr_destroy(bdr_ctx *c) {
     for (auto e : c->pool) cudaEventDestroy(e);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
+    for (auto e : c->chunk_events) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -1030,29 +1085,34 @@ int bdr_vacuum_assign(bdr_ctx *c, double vac_tol, double voxel_volume, int which
     return 0;
 }
 
-int bdr_bader_calc(bdr_ctx *c, int method, const double *dist_mat, const double *T_grad,
-                   int64_t *n_maxima) {
-    TRY(check(c));
-    if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_bader_calc: reference density not uploaded");
+static int bader_calc_dev(bdr_ctx *c, int method, const double *dist_mat, const double *T_grad,
+                          int64_t *n_maxima, const double *host_density) {
     if (!dist_mat) return fail_msg("bdr_bader_calc: dist_mat is null");
+    if (method != BDR_METHOD_ONGRID && method != BDR_METHOD_NEARGRID)
+        return fail_msg("bdr_bader_calc: unknown method");
+    if (method == BDR_METHOD_NEARGRID && !T_grad) return fail_msg("bdr_bader_calc: T_grad is null");
     const Weights W = make_weights(dist_mat);
-    if (method == BDR_METHOD_ONGRID) {
-        TRY(ongrid_dev(c, W));
-    } else if (method == BDR_METHOD_NEARGRID) {
-        if (!T_grad) return fail_msg("bdr_bader_calc: T_grad is null");
+    int64_t seeded = -1;
+    if (host_density) TRY(upload_and_stencil_dev(c, host_density, W, &seeded));
+    if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_bader_calc: reference density not uploaded");
+    TRY(ongrid_dev(c, W, seeded));
+    if (method == BDR_METHOD_NEARGRID) {
         const TGrad T = make_tgrad(T_grad);
-        // seed with the pointer-jumpable ongrid field, then drive the order-free
+        // seeded with the pointer-jumpable ongrid field; now drive the order-free
         // refinement iteration to its fixed point
-        TRY(ongrid_dev(c, W));
         TRY(converge_dev(c, BDR_LABELS_BADER, W, T));
         TRY(renumber_dev(c, BDR_LABELS_BADER));
-    } else {
-        return fail_msg("bdr_bader_calc: unknown method");
     }
     c->vac_mode = VAC_LABELS;
     if (n_maxima) *n_maxima = c->n_max;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int bdr_bader_calc(bdr_ctx *c, int method, const double *dist_mat, const double *T_grad,
+                   int64_t *n_maxima) {
+    TRY(check(c));
+    return bader_calc_dev(c, method, dist_mat, T_grad, n_maxima, nullptr);
 }
 
 int bdr_get_maxima(bdr_ctx *c, int64_t *out, int64_t cap) {
@@ -1191,14 +1251,14 @@ int bdr_run(bdr_ctx *c, const double *host_density, double vac_tol, double voxel
             void *host_labels, int label_elem_size, int64_t *n_maxima, int64_t *maxima,
             int64_t max_cap, double *charge, double *volume) {
     TRY(check(c));
-    TRY(bdr_upload_density(c, BDR_RHO_REFERENCE, host_density));
-    TRY(bdr_clear_labels(c, BDR_LABELS_BADER));
-    if (vac_tol == vac_tol) {
-        double q, v;
-        TRY(bdr_vacuum_assign(c, vac_tol, voxel_volume, BDR_RHO_REFERENCE, &q, &v));
-    }
+    if (!host_density) return fail_msg("bdr_run: host_density is null");
+    // volumes_init: labels start at 0; the vacuum mask (reference <= tol) is
+    // applied by the stencil pass itself
+    TRY(ensure_labels(c, BDR_LABELS_BADER));
+    c->vac_mode = (vac_tol == vac_tol) ? VAC_TOL : VAC_NONE;
+    c->vac_tol = vac_tol;
     int64_t n = 0;
-    TRY(bdr_bader_calc(c, method, dist_mat, T_grad, &n));
+    TRY(bader_calc_dev(c, method, dist_mat, T_grad, &n, host_density));
     if (refine_iters != 0) {
         int64_t run = 0;
         TRY(bdr_refine(c, BDR_LABELS_BADER, refine_mode, refine_iters, dist_mat, T_grad, &run,

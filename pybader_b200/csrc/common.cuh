@@ -83,6 +83,8 @@ struct ProfRec {
 struct bdr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // host -> device chunks of bdr_run
+    std::vector<cudaEvent_t> chunk_events;
     bdr::Grid g{0, 0, 0};
     int64_t N = 0;
     int halo = 0;               // slab windows: extra x planes on each side (0 = periodic grid)

@@ -355,3 +355,24 @@ def test_shared_reciprocal_division_is_ieee():
         check(e.lib.bdr_selftest_div(e.h, 1 << 24, seed, ctypes.byref(bad)))
         assert bad.value == 0
     e.close()
+
+
+@pytest.mark.parametrize('method,mode', [('ongrid', ('all', 0)), ('neargrid', ('changed', 2))])
+def test_one_shot_run_equals_staged(th, ut, seeded, method, mode):
+    """bdr_run (host buffers in, pipelined upload + stencil, host buffers out)
+    gives exactly what the stage-by-stage entry points give"""
+    from pybader_b200.engine import Engine
+    s = seeded
+    mx, vol = th.bader_calc(method, s['rho'], gpu_fresh(ut, s), s['dist_mat'], s['T_grad'], 1)
+    th.refine('neargrid', mode, s['rho'], vol, s['dist_mat'], s['T_grad'], 1)
+    n = mx.shape[0]
+    q, v = np.zeros(n), np.zeros(n)
+    ut.charge_sum(q, v, s['voxel_volume'], s['rho'], vol)
+    e = Engine(s['rho'].shape)
+    lab, mx2, q2, v2 = e.run(s['rho'], s['vacuum_tol'], s['voxel_volume'], method, mode[0], mode[1],
+                             s['dist_mat'], s['T_grad'], label_dtype=vol.dtype)
+    e.close()
+    np.testing.assert_array_equal(mx2, mx)
+    np.testing.assert_array_equal(lab, vol)
+    np.testing.assert_allclose(q2, q, rtol=1e-12)
+    np.testing.assert_allclose(v2, v, rtol=1e-12)
