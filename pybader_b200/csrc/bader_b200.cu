@@ -346,6 +346,13 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
     c->list_n = n;  // every candidate of the window; the trace kernel skips what it does not own
     *edges = 0;
     if (n == 0) return 0;
+    if (sticky_mode != 0) {
+        // conservative passes inside bader_calc('neargrid') skip the density half:
+        // a candidate that is a maximum merely stays listed (its trace ends on
+        // itself at once) and non-interior, which is the safe side
+        *edges = n;
+        return 0;
+    }
     // density half of the classification: drop the candidates that are maxima
     TRY(ensure(&c->list3, &c->list3_cap, 4096));
     for (int attempt = 0; attempt < 2; ++attempt) {
