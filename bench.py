@@ -42,7 +42,7 @@ SHAPES = {1: (1024, 1024, 1024), 2: (2048, 1024, 1024), 4: (2048, 2048, 1024),
           8: (2048, 2048, 2048)}
 
 # algorithmic bytes per voxel of each streaming kernel family
-ALG_BYTES = {'stencil': 12, 'resolve': 8, 'relabel': 8, 'edge_flag': 5, 'edge_dilate': 2,
+ALG_BYTES = {'stencil': 12, 'resolve': 8, 'relabel': 8, 'edge_flag': 4.25, 'edge_dilate': 1.25,
              'first': 4, 'charge_sum': 12, 'vacuum': 12, 'narrow': 5}
 
 
@@ -194,6 +194,38 @@ def workload_name(shape):
             f"refine('changed',2)")
 
 
+def kernel_accounting(prof, n_voxels, steps, tsteps, tvox, ms_per_step):
+    """per-family table (CUDA-event times on the library's stream) and the roofline
+    object of the family that takes the largest share of the step; n_voxels is what
+    one launch of a streaming kernel covers (the rank's grid or window)"""
+    peak, peak_src = peaks()
+    kernels = {}
+    for name, (ms, n) in prof.items():
+        k = {"ms_per_step": ms / steps, "launches_per_step": n / steps}
+        if name in ALG_BYTES:
+            gb = ALG_BYTES[name] * n_voxels * 1e-9
+            k["alg_bytes_per_voxel"] = ALG_BYTES[name]
+            k["achieved_gbs"] = gb / (ms / n * 1e-3)
+            k["frac"] = k["achieved_gbs"] / peak
+        kernels[name] = k
+    if 'trace' in kernels and tvox:
+        # gather-bound: 7 fp64 gathers + 1 known byte per trajectory step, label R+W per voxel
+        tb = tsteps * (7 * 8 + 1) + tvox * (4 + 4 + 4 + 1)
+        kernels['trace'].update({"alg_bytes_per_launch": tb / prof['trace'][1],
+                                 "achieved_gbs": tb * 1e-9 / (prof['trace'][0] * 1e-3),
+                                 "steps_per_voxel": tsteps / tvox,
+                                 "voxels_per_step": tvox / steps})
+        kernels['trace']["frac"] = kernels['trace']["achieved_gbs"] / peak
+    dom = max((k for k in kernels if 'achieved_gbs' in kernels[k]),
+              key=lambda k: kernels[k]['ms_per_step'])
+    dk = kernels[dom]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": dk['achieved_gbs'], "peak": peak,
+                "unit": "GB/s", "frac": dk['achieved_gbs'] / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": dk['ms_per_step'] / dk['launches_per_step'],
+                "share_of_step": dk['ms_per_step'] / ms_per_step}
+    return kernels, roofline
+
+
 # ---------------------------------------------------------------- GPU arm ----
 def main():
     ap = argparse.ArgumentParser()
@@ -204,7 +236,7 @@ def main():
     ap.add_argument('--size', type=int, default=0, help='override: cubic N^3 single-GPU grid')
     ap.add_argument('--cpu-sample', type=int, default=176)
     ap.add_argument('--ref-sample', type=int, default=112)
-    ap.add_argument('--halo', type=int, default=8)
+    ap.add_argument('--halo', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -267,31 +299,7 @@ def main():
     value = N / (ms_per_step * 1e-3)
 
     # ---- per-kernel accounting and the roofline object ---------------------
-    peak, peak_src = peaks()
-    kernels = {}
-    for name, (ms, n) in prof.items():
-        k = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps}
-        if name in ALG_BYTES:
-            gb = ALG_BYTES[name] * N * 1e-9
-            k["alg_bytes_per_voxel"] = ALG_BYTES[name]
-            k["achieved_gbs"] = gb / (ms / n * 1e-3)
-            k["frac"] = k["achieved_gbs"] / peak
-        kernels[name] = k
-    if 'trace' in kernels and tvox:
-        # gather-bound: 7 fp64 gathers + 1 known byte per trajectory step, label R+W per voxel
-        tb = tsteps * (7 * 8 + 1) + tvox * (4 + 4 + 4 + 1)
-        kernels['trace'].update({"alg_bytes_per_launch": tb / prof['trace'][1],
-                                 "achieved_gbs": tb * 1e-9 / (prof['trace'][0] * 1e-3),
-                                 "steps_per_voxel": tsteps / tvox,
-                                 "voxels_per_step": tvox / args.steps})
-        kernels['trace']["frac"] = kernels['trace']["achieved_gbs"] / peak
-    dom = max((k for k in kernels if 'achieved_gbs' in kernels[k]),
-              key=lambda k: kernels[k]['ms_per_step'])
-    dk = kernels[dom]
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": dk['achieved_gbs'], "peak": peak,
-                "unit": "GB/s", "frac": dk['achieved_gbs'] / peak, "traffic": None,
-                "peak_source": peak_src, "ms_per_launch": dk['ms_per_step'] / dk['launches_per_step'],
-                "share_of_step": dk['ms_per_step'] / ms_per_step}
+    kernels, roofline = kernel_accounting(prof, N, args.steps, tsteps, tvox, ms_per_step)
 
     # ---- e2e: host buffers through bdr_run -------------------------------------
     e2e = None

@@ -509,27 +509,84 @@ def bench(args, rank, world, local):
         sb.neargrid(dm, T)                 # ongrid seed + exits + numbering + rounds to quiescence
         return sb.refine(dm, T, 2)         # the caller's refine(): full pass(es)
 
+    be = sb.backend
+    dev = torch.device('cuda', local)
     for _ in range(args.warmup):
         hist = step()
     clocks = B.ClockSampler(local)
     if rank == 0:
         clocks.start()
+    be.check(be.lib.bdr_profile_enable(be.h, 1))
+    be.check(be.lib.bdr_profile_reset(be.h))
     torch.cuda.synchronize()
     dist.barrier()
-    l0 = sb.backend.launch_count()
-    sb.backend.timer_start()
+    l0 = be.launch_count()
+    be.timer_start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         hist = step()
-    ms = sb.backend.timer_stop()
+    ms = be.timer_stop()
     torch.cuda.synchronize()
     dist.barrier()
     wall = (time.perf_counter() - t0) * 1e3
-    launches = sb.backend.launch_count() - l0
-    ms = comm.allreduce_max(ms, torch.device('cuda', local))
-    launches = comm.allreduce_sum(launches, torch.device('cuda', local))
+    launches = be.launch_count() - l0
+    prof = {}
+    for i, name in enumerate(B_FAMILIES()):
+        pm, pn = ctypes.c_double(0), ctypes.c_int64(0)
+        be.check(be.lib.bdr_profile_get(be.h, i, ctypes.byref(pm), ctypes.byref(pn)))
+        if pn.value:
+            prof[name] = (pm.value, pn.value)
+    ts, tv = ctypes.c_int64(0), ctypes.c_int64(0)
+    be.check(be.lib.bdr_trace_steps(be.h, ctypes.byref(ts), ctypes.byref(tv)))
+    be.check(be.lib.bdr_profile_enable(be.h, 0))
+    clock_info = clocks.stop() if rank == 0 else None
+    ms = comm.allreduce_max(ms, dev)
+    launches = comm.allreduce_sum(launches, dev)
+    ms_per_step = ms / args.steps
+
+    # ---- e2e: every rank uploads its slab window from pinned host memory, runs the
+    # step and reads its labels back (narrowed like thread_handlers.bader_calc does)
+    e2e = None
+    if not args.no_e2e:
+        from .utils import dtype_calc
+        ldt = np.dtype(dtype_calc(-max(int(sb.maxima.shape[0]), 1)))
+        nwin = be.N
+        try:
+            host_rho = torch.empty(nwin, dtype=torch.float64, pin_memory=True).numpy()
+            host_lab = torch.empty(nwin * ldt.itemsize, dtype=torch.uint8, pin_memory=True).numpy()
+            ok = 1
+        except RuntimeError:
+            ok = 0
+        if comm.allreduce_sum(ok, dev) != world:
+            args.no_e2e = True
+    if not args.no_e2e:
+        be.check(be.lib.bdr_download_density(be.h, 0, host_rho.ctypes.data))
+
+        def e2e_step():
+            be._sync()
+            be.check(be.lib.bdr_upload_density(be.h, 0, host_rho.ctypes.data))
+            h = step()
+            be._sync()
+            be.check(be.lib.bdr_download_labels(be.h, 0, host_lab.ctypes.data, ldt.itemsize))
+            return h
+
+        e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        dt = comm.allreduce_max(dt, dev)
+        e2e = {"value": N / dt, "unit": B.UNIT, "h2d_bytes_per_step": nwin * 8 * world,
+               "d2h_bytes_per_step": nwin * ldt.itemsize * world, "ms_per_step": dt * 1e3,
+               "api": "per rank: bdr_upload_density(window, pinned host) + sharded step + "
+                      "bdr_download_labels(narrowed); max over ranks"}
+        del host_rho, host_lab
     if rank == 0:
-        ms_per_step = ms / args.steps
+        kernels, roofline = B.kernel_accounting(prof, be.N, args.steps, ts.value, tv.value, ms_per_step)
+        roofline["note"] = "rank 0's kernels on its slab window; the step also holds NCCL exchanges"
         out = {
             "metric": B.METRIC, "value": N / (ms_per_step * 1e-3), "unit": B.UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -538,13 +595,20 @@ def bench(args, rank, world, local):
             "config": {"workload": B.workload_name(shape), "atoms": len(case['amps']),
                        "maxima": int(sb.maxima.shape[0]), "method": "neargrid",
                        "refine_method": "neargrid", "refine_mode": ["all", 2],
-                       "parallelism": f"{world} x-slabs, halo {args.halo} planes, NCCL ring exchange",
+                       "parallelism": f"{world} x-slabs, halo {args.halo} planes, NCCL ring exchange "
+                                      f"of halo planes / exit labels, NVLink peer loads in the trace",
                        "l2": "per-GPU inputs are far larger than the 126 MB L2; no flush"},
-            "roofline": None, "cpu_baseline": None,
-            "e2e": None, "gpu_launches": launches, "clocks": clocks.stop(),
-            "wall_ms_per_step": wall / args.steps, "refine_history_last_step": hist,
+            "roofline": roofline, "cpu_baseline": None,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+            "wall_ms_per_step": wall / args.steps, "kernels": kernels,
+            "refine_history_last_step": hist,
             "exit_rounds": sb.exit_rounds, "neargrid_passes": len(sb.neargrid_history),
             "neargrid_settled": sb.settled,
         }
         print(json.dumps(out))
     dist.destroy_process_group()
+
+
+def B_FAMILIES():
+    from .engine import FAMILIES
+    return FAMILIES

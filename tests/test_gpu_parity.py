@@ -376,3 +376,139 @@ def test_one_shot_run_equals_staged(th, ut, seeded, method, mode):
     np.testing.assert_array_equal(lab, vol)
     np.testing.assert_allclose(q2, q, rtol=1e-12)
     np.testing.assert_allclose(v2, v, rtol=1e-12)
+
+
+# ------------------------------------- BASELINE configs 3 and 4 at full size ----
+def _properties(e, lab, mx, dV, vac_count=0, check_order=True):
+    from pybader_b200.engine import LABELS_BADER
+    n = mx.shape[0]
+    flat = lab.ravel()
+    assert flat.min() == (-1 if vac_count else 0) and flat.max() == n - 1
+    assert int((flat == -1).sum()) == vac_count
+    # every maximum carries its own number; numbers ascend with the first voxel
+    assert [int(lab[tuple(m)]) for m in mx] == list(range(n))
+    if check_order:
+        first = np.full(n, flat.size, dtype=np.int64)
+        step = 1 << 24
+        for lo in range(0, flat.size, step):
+            vals, idx = np.unique(flat[lo:lo + step], return_index=True)
+            keep = vals >= 0
+            np.minimum.at(first, vals[keep], idx[keep] + lo)
+        assert np.all(np.diff(first) > 0)
+    q, v = np.zeros(n), np.zeros(n)
+    e.charge_sum(LABELS_BADER, 0, dV, q, v)
+    return q, v
+
+
+def test_config3_triclinic_vacuum_full_size():
+    """BASELINE config 3: triclinic 128-atom cell 360x360x480, vacuum_tol 1e-3,
+    neargrid + refine ('changed', 2): size-independent properties"""
+    from pybader_b200 import geometry as geo, synth
+    from pybader_b200.engine import Engine, LABELS_BADER
+    c = synth.case_triclinic((360, 360, 480), n_atoms=128, seed=1234)
+    shape = c['shape']
+    e = Engine(shape)
+    e.synth_general(0, c['lattice'], c['frac_atoms'], c['amps'], c['sigmas'])
+    dist = geo.distance_matrix(c['lattice'], shape)
+    T = geo.T_grad(c['lattice'], shape)
+    dV = geo.voxel_volume(c['lattice'], shape)
+    rho = e.download_density(0)
+    tol = 1e-3
+    nvac = int((rho <= tol).sum())
+    assert 0 < nvac < rho.size
+    e.clear_labels()
+    vq, vv = e.vacuum_assign(tol, dV)
+    assert vv == pytest.approx(nvac * dV, rel=1e-12)
+    assert vq == pytest.approx(rho[rho <= tol].sum() * dV, rel=1e-9)
+    mx_on = e.bader_calc('ongrid', dist, T)
+    lab_on = e.download_labels(LABELS_BADER, np.int32)
+    q_on, v_on = _properties(e, lab_on, mx_on, dV, nvac)
+    assert q_on.sum() + vq == pytest.approx(rho.sum() * dV, rel=1e-10)
+    # ongrid pointers are a pure function of the density: spot-check 400 voxels on the CPU
+    rng = np.random.default_rng(7)
+    W = np.array([[[dist[i, j, k] for k in (-1, 0, 1)] for j in (-1, 0, 1)] for i in (-1, 0, 1)])
+    for x, y, z in rng.integers(0, shape, size=(400, 3)):
+        if lab_on[x, y, z] < 0:
+            continue
+        p = (x, y, z)
+        for _ in range(4000):
+            rc, best, nxt = rho[p], rho[p], p
+            for ix in (-1, 0, 1):
+                for iy in (-1, 0, 1):
+                    for iz in (-1, 0, 1):
+                        q = ((p[0] + ix) % shape[0], (p[1] + iy) % shape[1], (p[2] + iz) % shape[2])
+                        val = (rho[q] - rc) * W[ix + 1, iy + 1, iz + 1] + rc
+                        if val > best:
+                            best, nxt = val, q
+            if nxt == p:
+                break
+            p = nxt
+        assert lab_on[p] == lab_on[x, y, z] and tuple(mx_on[lab_on[p]]) == p
+    # neargrid + refine: same maxima, quiescent, vacuum untouched by 'all' mode
+    e.clear_labels()
+    e.vacuum_assign(tol, dV)
+    mx = e.bader_calc('neargrid', dist, T)
+    assert sorted(map(tuple, mx.tolist())) == sorted(map(tuple, mx_on.tolist()))
+    hist = e.refine(LABELS_BADER, 'changed', 2, dist, T)
+    assert hist[0][1] <= 1e-5 * rho.size
+    lab = e.download_labels(LABELS_BADER, np.int32)
+    q, v = np.zeros(len(mx)), np.zeros(len(mx))
+    e.charge_sum(LABELS_BADER, 0, dV, q, v)
+    # 'changed' mode may hand a few vacuum voxels to volumes (reference quirk, SURVEY A.5)
+    moved = nvac - int((lab == -1).sum())
+    assert 0 <= moved <= 1e-5 * rho.size
+    assert v.sum() == pytest.approx((rho.size - nvac + moved) * dV, rel=1e-12)
+    assert np.mean((lab >= 0) == (lab_on >= 0)) > 0.99999
+    # neargrid and ongrid partitions agree away from the surfaces
+    order = {tuple(m): i for i, m in enumerate(mx_on.tolist())}
+    perm = np.array([order[tuple(m)] for m in mx.tolist()])
+    same = np.where(lab >= 0, perm[np.maximum(lab, 0)], -1) == lab_on
+    assert same.mean() > 0.97
+    e.close()
+
+
+def test_config4_slab_spin_full_size():
+    """BASELINE config 4: 512x512x1024 slab with vacuum and a spin density"""
+    from pybader_b200 import geometry as geo, synth
+    from pybader_b200.engine import Engine, LABELS_ATOMS, LABELS_BADER
+    c = synth.case_slab((512, 512, 1024), n_atoms=64, seed=4321)
+    shape = c['shape']
+    e = Engine(shape)
+    tx, ty, tz = synth.separable_tables(c)
+    e.synth_separable(0, tx, ty, tz)
+    e.synth_separable(2, tx * c['spin_weights'][:, None], ty, tz)
+    dist = geo.distance_matrix(c['lattice'], shape)
+    T = geo.T_grad(c['lattice'], shape)
+    dV = geo.voxel_volume(c['lattice'], shape)
+    tol = 1e-3
+    e.clear_labels()
+    vq, vv = e.vacuum_assign(tol, dV)
+    nvac = round(vv / dV)
+    assert 0 < nvac < np.prod(shape)
+    mx = e.bader_calc('neargrid', dist, T)
+    hist = e.refine(LABELS_BADER, 'all', 2, dist, T)
+    assert hist[0][1] <= 1e-5 * np.prod(shape) and hist[-1][1] <= hist[0][1]
+    lab = e.download_labels(LABELS_BADER, np.int32)
+    n = len(mx)
+    assert 32 <= n <= 64          # close Gaussians merge into one maximum
+    q, v = _properties(e, lab, mx, dV, nvac, check_order=False)
+    assert v.sum() == pytest.approx((np.prod(shape) - nvac) * dV, rel=1e-12)
+    s, v2 = np.zeros(n), np.zeros(n)
+    e.charge_sum(LABELS_BADER, 2, dV, s, v2)
+    np.testing.assert_array_equal(v2, v)
+    # atoms: every maximum goes to its nearest atom; per-atom sums == sums of their volumes
+    atoms = c['frac_atoms'] @ c['lattice']
+    off = np.array([.5, .5, .5])                              # cube files, io/cube.py:154
+    mcart = geo.maxima_fractional(mx, shape, off) @ c['lattice']
+    who, d = e.assign_atoms(mcart, atoms, c['lattice'])
+    assert who.min() >= 0 and who.max() < 64 and np.all(d >= 0)
+    qa, va = np.zeros(64), np.zeros(64)
+    e.charge_sum(LABELS_ATOMS, 0, dV, qa, va)
+    np.testing.assert_allclose(qa, np.bincount(who, weights=q, minlength=64), rtol=1e-9)
+    np.testing.assert_allclose(va, np.bincount(who, weights=v, minlength=64), rtol=1e-9)
+    sa, _ = np.zeros(64), np.zeros(64)
+    e.charge_sum(LABELS_ATOMS, 2, dV, sa, _)
+    np.testing.assert_allclose(sa, np.bincount(who, weights=s, minlength=64), rtol=1e-7, atol=1e-9)
+    sd = e.surface_distance(LABELS_ATOMS, c['lattice'], atoms)
+    assert sd is not None and np.all(sd[np.bincount(who, minlength=64) > 0] > 0)
+    e.close()
