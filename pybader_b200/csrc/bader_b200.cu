@@ -443,7 +443,8 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
         LAUNCH(c, BDR_K_TRACE, (k_trace_peer<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
                *pv, c->labels[which], c->known, c->g, window_of(c), W, T, c->list, n, chunk,
                (long long *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
-               c->list2_cap, c->list3, c->list3_cap, step_cap);
+               c->list2_cap, c->list3, c->list3_cap, step_cap,
+               c->use_term ? c->term : (int32_t *)nullptr);
     else
         LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
                rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c), W, T,
@@ -466,7 +467,8 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
                        c->labels[which], c->known, c->g, window_of(c), W, T, c->list3 + o, m, 32,
                        (long long *)c->stage, c->d_cnt,
                        want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
-                       (int32_t *)nullptr, (int64_t)0, step_cap);
+                       (int32_t *)nullptr, (int64_t)0, step_cap,
+                       c->use_term ? c->term : (int32_t *)nullptr);
             else
                 LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
                        rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
@@ -843,7 +845,7 @@ int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *
 int bdr_slab_first_voxel(bdr_ctx *c, int64_t n_slots, int32_t *dev_out) {
     TRY(check(c));
     CU(cudaMemsetAsync(dev_out, 0x7f, (size_t)n_slots * sizeof(int32_t), c->stream));
-    LAUNCH(c, BDR_K_FIRST, k_first_voxel_slots, blocks_for(c->own_hi - c->own_lo, 256), 256, 0,
+    LAUNCH(c, BDR_K_FIRST, k_first_voxel_slots, blocks_for(c->own_hi - c->own_lo, 1024), 256, 0,
            c->labels[BDR_LABELS_BADER], (int)c->own_lo, (int)c->own_hi, dev_out);
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -876,6 +878,10 @@ int bdr_slab_first_pass(bdr_ctx *c, int which, int64_t *edges) {
     int64_t e = 0;
     TRY(edge_find_dev(c, which, &e, -1, 1));
     c->last_changed = 0;
+    // trajectory-end cache for the rounds that follow (see converge_dev)
+    if (!c->term) CU(cudaMalloc((void **)&c->term, (size_t)c->N * sizeof(int32_t)));
+    CU(cudaMemsetAsync(c->term, 0xff, (size_t)c->N * sizeof(int32_t), c->stream));
+    c->use_term = true;
     CU(cudaStreamSynchronize(c->stream));
     if (edges) *edges = e;
     return 0;
@@ -925,6 +931,7 @@ int bdr_slab_requeue(bdr_ctx *c, int which, const int32_t *dev_extra, int64_t n_
     } else {
         TRY(incremental_dev(c, which, n, &q));
     }
+    if (c->use_term) TRY(filter_cached_dev(c));
     q = c->list_n;
     CU(cudaStreamSynchronize(c->stream));
     if (queued) *queued = q;
@@ -936,6 +943,7 @@ int bdr_trace_pass(bdr_ctx *c, int which, const double *dist_mat, const double *
     TRY(check(c));
     if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_trace_pass: bad label set");
     if (!c->known) return fail_msg("bdr_trace_pass: run bdr_edge_pass first");
+    c->use_term = false;  // an exact pass: nothing cached applies
     const Weights W = make_weights(dist_mat);
     const TGrad T = make_tgrad(T_grad);
     int64_t ch = 0;
