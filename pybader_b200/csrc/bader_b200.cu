@@ -255,17 +255,18 @@ static int upload_and_stencil_dev(bdr_ctx *c, const double *host, const Weights 
     return 0;
 }
 
-static int ongrid_dev(bdr_ctx *c, const Weights &W_full, int64_t seeded = -1) {
-    if (c->halo > 0) return fail_msg("bader_calc: slab windows are driven through the bdr_slab_* entry points");
-    int64_t n = seeded;  // >= 0: the stencil pass already ran (bdr_run's pipelined upload)
-    if (n < 0) TRY(stencil_dev(c, W_full, &n));
-    int32_t *code = c->labels[BDR_LABELS_BADER];
-    c->n_max = n;
-    c->maxima.assign((size_t)n * 3, 0);
+// slot codes -> volume numbers: volumes are numbered by their first voxel in C
+// order, which is the reference's order of discovery.  With
+// have_first the resolve pass has already filled c->minidx.
+static int number_slots_dev(bdr_ctx *c, bool have_first) {
+    const int64_t n = c->n_max;
     if (n == 0) return 0;
-    CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
-    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, code, c->N, c->minidx,
-           getenv("BDR_RESOLVE_MODE") ? atoi(getenv("BDR_RESOLVE_MODE")) : 3);
+    int32_t *code = c->labels[BDR_LABELS_BADER];
+    if (!have_first) {
+        CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
+        LAUNCH(c, BDR_K_FIRST, k_first_voxel_slots, blocks_for(c->N, 1024), 256, 0, code, 0, (int)c->N,
+               c->minidx);
+    }
     std::vector<int32_t> order;
     TRY(rank_from_first(c, n, order, nullptr));
     std::vector<int32_t> roots((size_t)n);
@@ -273,6 +274,7 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full, int64_t seeded = -1) {
                        c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const int64_t nyz = (int64_t)c->g.ny * c->g.nz;
+    c->maxima.assign((size_t)n * 3, 0);
     for (int64_t r = 0; r < n; ++r) {
         const int64_t v = roots[(size_t)order[(size_t)r]];
         c->maxima[(size_t)r * 3 + 0] = v / nyz;
@@ -283,24 +285,22 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full, int64_t seeded = -1) {
     return 0;
 }
 
-// renumber an already numbered label array by first voxel; permutes maxima too
-static int renumber_dev(bdr_ctx *c, int which) {
-    const int64_t n = c->n_max;
+// stencil -> pointer codes -> resolved slot codes (-2 - slot; vacuum -1).  With
+// `number` the codes are then turned into volume numbers; bader_calc('neargrid')
+// keeps the codes as labels through its rounds and numbers once at the end.
+static int ongrid_dev(bdr_ctx *c, const Weights &W_full, int64_t seeded = -1, bool number = true) {
+    if (c->halo > 0) return fail_msg("bader_calc: slab windows are driven through the bdr_slab_* entry points");
+    int64_t n = seeded;  // >= 0: the stencil pass already ran (bdr_run's pipelined upload)
+    if (n < 0) TRY(stencil_dev(c, W_full, &n));
+    int32_t *code = c->labels[BDR_LABELS_BADER];
+    c->n_max = n;
+    c->maxima.assign((size_t)n * 3, 0);
     if (n == 0) return 0;
-    CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
-    LAUNCH(c, BDR_K_FIRST, k_first_voxel, blocks_for(c->N, 1024), 256, 0, c->labels[which], c->N,
-           c->minidx);
-    std::vector<int32_t> order;
-    bool ident = true;
-    TRY(rank_from_first(c, n, order, &ident));
-    if (ident) return 0;
-    std::vector<int64_t> mx((size_t)n * 3);
-    for (int64_t r = 0; r < n; ++r)
-        for (int k = 0; k < 3; ++k)
-            mx[(size_t)r * 3 + k] = c->maxima[(size_t)order[(size_t)r] * 3 + k];
-    c->maxima.swap(mx);
-    LAUNCH(c, BDR_K_RELABEL, k_relabel_lut, blocks_for(c->N, 1024), 256, 0, c->labels[which],
-           c->labels[which], c->N, c->rank);
+    if (number) CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
+    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, code, c->N,
+           number ? c->minidx : (int32_t *)nullptr,
+           getenv("BDR_RESOLVE_MODE") ? atoi(getenv("BDR_RESOLVE_MODE")) : 3);
+    if (number) TRY(number_slots_dev(c, true));
     return 0;
 }
 
@@ -1110,13 +1110,14 @@ static int bader_calc_dev(bdr_ctx *c, int method, const double *dist_mat, const 
     int64_t seeded = -1;
     if (host_density) TRY(upload_and_stencil_dev(c, host_density, W, &seeded));
     if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_bader_calc: reference density not uploaded");
-    TRY(ongrid_dev(c, W, seeded));
+    TRY(ongrid_dev(c, W, seeded, method == BDR_METHOD_ONGRID));
     if (method == BDR_METHOD_NEARGRID) {
         const TGrad T = make_tgrad(T_grad);
-        // seeded with the pointer-jumpable ongrid field; now drive the order-free
-        // refinement iteration to its fixed point
+        // seeded with the pointer-jumpable ongrid field (still as slot codes, which
+        // serve as labels); now drive the order-free refinement iteration to its
+        // fixed point, then number the volumes once
         TRY(converge_dev(c, BDR_LABELS_BADER, W, T));
-        TRY(renumber_dev(c, BDR_LABELS_BADER));
+        TRY(number_slots_dev(c, false));
     }
     c->vac_mode = VAC_LABELS;
     if (n_maxima) *n_maxima = c->n_max;
