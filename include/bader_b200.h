@@ -225,7 +225,12 @@ int bdr_slab_ipc_attach(bdr_ctx *ctx, int world, int rank, const void *all_handl
  * 1 it additionally repeats full passes until one changes nothing, so the
  * labels are certified to be a fixed point of the reference's refinement
  * iteration before any refine() call.                                       */
-enum { BDR_OPT_VERIFY_FIXED_POINT = 0 };
+/* BDR_OPT_SLAB_SEED_METHOD (default BDR_METHOD_ONGRID): which method the next
+ * bdr_slab_seed serves.  'ongrid' needs the bit-exact fp64 argmax of
+ * methods.py:87-117; 'neargrid' only needs an ascending pointer field with the
+ * same maxima and takes the cheaper fp32-ranked stencil (as bdr_bader_calc
+ * does on one GPU, so sharded and single-GPU runs seed identically).        */
+enum { BDR_OPT_VERIFY_FIXED_POINT = 0, BDR_OPT_SLAB_SEED_METHOD = 1 };
 int bdr_set_option(bdr_ctx *ctx, int option, int64_t value);
 
 /* self test: the trace kernel divides three gradient components by one

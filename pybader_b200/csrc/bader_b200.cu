@@ -1,6 +1,7 @@
 // bader_b200.cu -- host side of libbader_b200.so: the C ABI declared in
 // include/bader_b200.h on top of the kernels in kernels.cuh.
 #include "kernels.cuh"
+#include "seed.cuh"
 
 #include <cstdlib>
 
@@ -39,6 +40,20 @@ static HalfWeights half_weights(const Weights &W) {
     HalfWeights h;
     for (int k = 0; k < 14; ++k) h.w[k] = W.w[k];
     return h;
+}
+// fp32 step weights of the neargrid seed (seed.cuh); false when the weights are
+// outside the range its "clearly uphill" argument covers (the exact kernel runs then)
+static bool seed_weights(const Weights &W, SeedWeights *out) {
+    double wmax = 0.0, wmin = 1e300;
+    for (int k = 0; k < 13; ++k) {
+        out->w[k] = (float)W.w[k];
+        wmax = std::max(wmax, W.w[k]);
+        wmin = std::min(wmin, W.w[k]);
+    }
+    out->c1 = (float)(std::ldexp(1.0, -21) * wmax * 1.0001);
+    out->floor_ = (float)(std::ldexp(1.0, -96) * wmax);
+    out->tag_mask = 0xfffffff0u;
+    return wmin > 1e-6 && wmax < 1e6 && wmax / wmin < 1e3;
 }
 static TGrad make_tgrad(const double *T) {
     TGrad t;
@@ -163,26 +178,112 @@ static int rank_from_first(bdr_ctx *c, int64_t n, std::vector<int32_t> &order, b
 // real maxima follow
 static int exit_base_of(const bdr_ctx *c) { return c->halo > 0 ? 2 * c->g.ny * c->g.nz : 0; }
 
-// the stencil pass over planes [x_begin, x_end) (x_begin a multiple of SX)
-static int stencil_launch(bdr_ctx *c, const HalfWeights &W, int x_begin, int x_end) {
-    const size_t smem = stencil_smem();
+// tiles of the last stencil pass (the resolve pass walks the same tiling)
+static int stencil_tx(const bdr_ctx *c) { return c->seed_f32 ? FX : SX; }
+static int stencil_ty(const bdr_ctx *c) { return c->seed_f32 ? FY : TY; }
+static int stencil_tz(const bdr_ctx *c) { return c->seed_f32 ? FZ : TZ; }
+static dim3 stencil_grid(const bdr_ctx *c) {
+    const int tx = stencil_tx(c), ty = stencil_ty(c), tz = stencil_tz(c);
+    return dim3((c->g.nz + tz - 1) / tz, (c->g.ny + ty - 1) / ty, (c->g.nx + tx - 1) / tx);
+}
+static int ensure_tiles(bdr_ctx *c) {
+    const dim3 gr = stencil_grid(c);
+    const int64_t n = (int64_t)gr.x * gr.y * gr.z;
+    if (!c->tile_hist) CU(cudaMalloc((void **)&c->tile_hist, 65536 * sizeof(unsigned)));
+    if (c->tiles_cap >= n) return 0;
+    if (c->tile_keys) cudaFree(c->tile_keys);
+    if (c->tile_order) cudaFree(c->tile_order);
+    c->tile_keys = nullptr;
+    c->tile_order = nullptr;
+    c->tiles_cap = 0;
+    CU(cudaMalloc((void **)&c->tile_keys, (size_t)n * sizeof(uint32_t)));
+    CU(cudaMalloc((void **)&c->tile_order, (size_t)n * sizeof(int32_t)));
+    c->tiles_cap = n;
+    return 0;
+}
+
+// the stencil pass over planes [x_begin, x_end) (x_begin a multiple of the tile depth)
+static int stencil_launch(bdr_ctx *c, const Weights &W_full, int x_begin, int x_end) {
     int32_t *code = c->labels[BDR_LABELS_BADER];
     const double *rho = rho_ptr(c, BDR_RHO_REFERENCE);
     const int xb = exit_base_of(c);
-    dim3 grid = tile_grid(c->g, SX);
-    grid.z = (x_end - x_begin + SX - 1) / SX;
+    dim3 grid = stencil_grid(c);
+    const int tx = stencil_tx(c);
+    grid.z = (x_end - x_begin + tx - 1) / tx;
     // vacuum comes from the fused tolerance test when the labels were made
     // by bdr_vacuum_assign / bdr_clear_labels on this handle, else from
     // the label array itself (-1 entries)
+    if (c->seed_f32) {
+        SeedWeights Wf;
+        seed_weights(W_full, &Wf);
+        const size_t smem = seed_smem();
+        if (c->vac_mode == VAC_NONE)
+            LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_NONE>), grid, 256, smem, rho, code, c->g, Wf,
+                   W_full, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin, c->tile_keys);
+        else if (c->vac_mode == VAC_TOL)
+            LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_TOL>), grid, 256, smem, rho, code, c->g, Wf,
+                   W_full, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
+                   c->tile_keys);
+        else
+            LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_LABELS>), grid, 256, smem, rho, code, c->g,
+                   Wf, W_full, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
+                   c->tile_keys);
+        return 0;
+    }
+    const HalfWeights W = half_weights(W_full);
+    const size_t smem = stencil_smem();
     if (c->vac_mode == VAC_NONE)
         LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_NONE>), grid, 256, smem, rho, code,
-               c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin);
+               c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin, c->tile_keys);
     else if (c->vac_mode == VAC_TOL)
         LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_TOL>), grid, 256, smem, rho, code,
-               c->g, W, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin);
+               c->g, W, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
+               c->tile_keys);
     else
         LAUNCH(c, BDR_K_STENCIL, (k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>), grid, 256, smem, rho,
-               code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin);
+               code, c->g, W, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
+               c->tile_keys);
+    return 0;
+}
+
+// which stencil kernel seeds this call: the fp32-ranked one for 'neargrid'
+// (seed.cuh), the bit-exact fp64 one for 'ongrid'
+static void choose_seed(bdr_ctx *c, int method, const Weights &W) {
+    SeedWeights Wf;
+    c->seed_f32 = method == BDR_METHOD_NEARGRID && seed_weights(W, &Wf) && !getenv("BDR_SEED_EXACT");
+}
+
+// pointer codes -> terminal codes, tile by tile in order of decreasing density
+// (seed.cuh K2); with minidx the first voxel of every slot is recorded on the way
+static int resolve_dev(bdr_ctx *c, int32_t *minidx) {
+    int32_t *code = c->labels[BDR_LABELS_BADER];
+    if (getenv("BDR_RESOLVE_OLD")) {
+        LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, code, c->N, minidx, 3);
+        return 0;
+    }
+    const dim3 gr = stencil_grid(c);
+    const int n = (int)(gr.x * gr.y * gr.z);
+    CU(cudaMemsetAsync(c->tile_hist, 0, 65536 * sizeof(unsigned), c->stream));
+    LAUNCH(c, BDR_K_RESOLVE, k_tile_hist, blocks_for(n, 256), 256, 0, c->tile_keys, n, c->tile_hist);
+    LAUNCH(c, BDR_K_RESOLVE, k_tile_scan, 1, 1024, 0, c->tile_hist);
+    LAUNCH(c, BDR_K_RESOLVE, k_tile_scatter, blocks_for(n, 256), 256, 0, c->tile_keys, n, c->tile_hist,
+           c->tile_order);
+    const bool vec = (c->g.nz & 3) == 0;
+    if (c->seed_f32) {
+        if (vec)
+            LAUNCH(c, BDR_K_RESOLVE, (k_resolve_tiles<FX, FY, FZ, true>), n, 256, 0, code, c->g,
+                   c->tile_order, (int)gr.x, (int)gr.y, minidx);
+        else
+            LAUNCH(c, BDR_K_RESOLVE, (k_resolve_tiles<FX, FY, FZ, false>), n, 256, 0, code, c->g,
+                   c->tile_order, (int)gr.x, (int)gr.y, minidx);
+    } else {
+        if (vec)
+            LAUNCH(c, BDR_K_RESOLVE, (k_resolve_tiles<SX, TY, TZ, true>), n, 256, 0, code, c->g,
+                   c->tile_order, (int)gr.x, (int)gr.y, minidx);
+        else
+            LAUNCH(c, BDR_K_RESOLVE, (k_resolve_tiles<SX, TY, TZ, false>), n, 256, 0, code, c->g,
+                   c->tile_order, (int)gr.x, (int)gr.y, minidx);
+    }
     return 0;
 }
 
@@ -191,7 +292,8 @@ static int stencil_dev(bdr_ctx *c, const Weights &W_full, int64_t *n_real) {
     TRY(ensure_slots(c, 4096));
     if (!weights_symmetric(W_full))
         return fail_msg("bader_calc: dist_mat[-d] != dist_mat[d]; not a step-length table");
-    const HalfWeights W = half_weights(W_full);
+    TRY(ensure_tiles(c));
+    const Weights &W = W_full;
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_ROOTS));
         TRY(stencil_launch(c, W, 0, c->g.nx));
@@ -219,8 +321,9 @@ static int upload_and_stencil_dev(bdr_ctx *c, const double *host, const Weights 
     TRY(ensure_slots(c, 4096));
     if (!weights_symmetric(W_full))
         return fail_msg("bader_calc: dist_mat[-d] != dist_mat[d]; not a step-length table");
-    const HalfWeights W = half_weights(W_full);
-    const int CH = 4 * SX;
+    TRY(ensure_tiles(c));
+    const Weights &W = W_full;
+    const int CH = 4 * stencil_tx(c);
     const int nchunks = (c->g.nx + CH - 1) / CH;
     if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     while ((int)c->chunk_events.size() < nchunks) {
@@ -292,14 +395,11 @@ static int ongrid_dev(bdr_ctx *c, const Weights &W_full, int64_t seeded = -1, bo
     if (c->halo > 0) return fail_msg("bader_calc: slab windows are driven through the bdr_slab_* entry points");
     int64_t n = seeded;  // >= 0: the stencil pass already ran (bdr_run's pipelined upload)
     if (n < 0) TRY(stencil_dev(c, W_full, &n));
-    int32_t *code = c->labels[BDR_LABELS_BADER];
     c->n_max = n;
     c->maxima.assign((size_t)n * 3, 0);
     if (n == 0) return 0;
     if (number) CU(cudaMemsetAsync(c->minidx, 0x7f, (size_t)n * sizeof(int32_t), c->stream));
-    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, code, c->N,
-           number ? c->minidx : (int32_t *)nullptr,
-           getenv("BDR_RESOLVE_MODE") ? atoi(getenv("BDR_RESOLVE_MODE")) : 3);
+    TRY(resolve_dev(c, number ? c->minidx : (int32_t *)nullptr));
     if (number) TRY(number_slots_dev(c, true));
     return 0;
 }
@@ -756,6 +856,12 @@ int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out) {
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
     CU(cudaFuncSetAttribute(k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_TOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_LABELS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)seed_smem()));
     *out = c;
     return 0;
 }
@@ -832,9 +938,9 @@ int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *
     if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_slab_seed: density not set");
     const Weights W = make_weights(dist_mat);
     int64_t n = 0;
+    choose_seed(c, c->slab_seed_method, W);
     TRY(stencil_dev(c, W, &n));
-    LAUNCH(c, BDR_K_RESOLVE, k_resolve, blocks_for(c->N, 1024), 256, 0, c->labels[BDR_LABELS_BADER],
-           c->N, (int32_t *)nullptr, 3);
+    TRY(resolve_dev(c, nullptr));
     CU(cudaStreamSynchronize(c->stream));
     c->n_max = n;
     if (n_real) *n_real = n;
@@ -964,7 +1070,8 @@ int bdr_destroy(bdr_ctx *c) {
         if (c->labels[i]) cudaFree(c->labels[i]);
     for (void *p : {(void *)c->known, (void *)c->list, (void *)c->list2, (void *)c->list3,
                     (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
-                    (void *)c->d_sums, c->stage, (void *)c->ebits, (void *)c->term})
+                    (void *)c->d_sums, c->stage, (void *)c->ebits, (void *)c->term,
+                    (void *)c->tile_keys, (void *)c->tile_order, (void *)c->tile_hist})
         if (p) cudaFree(p);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -1107,6 +1214,7 @@ static int bader_calc_dev(bdr_ctx *c, int method, const double *dist_mat, const 
         return fail_msg("bdr_bader_calc: unknown method");
     if (method == BDR_METHOD_NEARGRID && !T_grad) return fail_msg("bdr_bader_calc: T_grad is null");
     const Weights W = make_weights(dist_mat);
+    choose_seed(c, method, W);
     int64_t seeded = -1;
     if (host_density) TRY(upload_and_stencil_dev(c, host_density, W, &seeded));
     if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_bader_calc: reference density not uploaded");
@@ -1404,6 +1512,11 @@ int bdr_set_option(bdr_ctx *c, int option, int64_t value) {
     TRY(check(c));
     switch (option) {
         case BDR_OPT_VERIFY_FIXED_POINT: c->verify_fixed_point = value != 0; return 0;
+        case BDR_OPT_SLAB_SEED_METHOD:
+            if (value != BDR_METHOD_ONGRID && value != BDR_METHOD_NEARGRID)
+                return fail_msg("bdr_set_option: unknown method");
+            c->slab_seed_method = (int)value;
+            return 0;
     }
     return fail_msg("bdr_set_option: unknown option");
 }

@@ -120,6 +120,12 @@ struct bdr_ctx {
     int32_t *minidx = nullptr; // first voxel (C order) of each slot's volume
     int32_t *rank = nullptr;   // slot -> volume number
     int64_t slots_cap = 0;
+    bool seed_f32 = false;         // the last stencil pass was the fp32-ranked seed (seed.cuh)
+    int slab_seed_method = 0;      // BDR_OPT_SLAB_SEED_METHOD
+    uint32_t *tile_keys = nullptr; // largest density of every stencil tile (resolve order)
+    int32_t *tile_order = nullptr;
+    unsigned *tile_hist = nullptr;
+    int64_t tiles_cap = 0;
     std::vector<int64_t> maxima;  // [n][3], in volume-number order
     int64_t n_max = 0;
 

@@ -1,0 +1,405 @@
+// seed.cuh -- the pointer-jumpable seed of bader_calc('neargrid') and the
+// tile-ordered pointer resolution shared by both methods.
+//
+// bader_calc('neargrid') only needs *a* strictly-ascending pointer field whose
+// terminal voxels are exactly the ongrid maxima (methods.py:169-177): the
+// labels it seeds are then driven to the fixed point of the reference's own
+// refinement iteration, which does not depend on which
+// ascending neighbour a seed pointer chose.  k_ongrid_pointers (kernels.cuh)
+// pays ~340 issue slots per voxel for the bit-exact fp64 argmax the 'ongrid'
+// method needs; the seed kernel here ranks the neighbours in fp32 instead:
+//
+//   * the density tile is converted to fp32 once while it is staged in shared
+//     memory (half the shared memory, 64-bit loads feed two voxels);
+//   * neighbours k and 26-k share a step weight, so only the larger of each
+//     pair is scored: 13 x (FMNMX, FADD, FMUL, LOP3, FMNMX) per voxel, the
+//     pair index riding in the four low mantissa bits of the score;
+//   * the winner is accepted only when it is *clearly* uphill in fp32
+//     (difference >= 2 fp32 ulps of the centre), which implies the exact fp64
+//     ongrid criterion (rho_n - rho_c) * w + rho_c > rho_c for that neighbour;
+//     anything else -- maxima, plateaus, denormal densities -- takes the exact
+//     fp64 27-point evaluation of methods.py:87-117 from global memory.
+//
+// So every pointer goes strictly uphill in the exact density (the field is
+// acyclic), and a voxel is a maximum here iff the reference's ongrid step
+// says so.  All decisions are functions of the voxel's own neighbourhood, so
+// slab windows of a sharded run produce the same pointers as one GPU.
+#pragma once
+#include "kernels.cuh"
+
+namespace bdr {
+
+constexpr int FX = 12, FY = 8, FZ = 64;  // seed tile: 256 threads x (2 z voxels) x 12 planes
+constexpr int F_HX = FX + 2, F_HY = FY + 2, F_RS = 68, F_TILE = FX * FY * FZ;
+constexpr size_t seed_smem() {
+    return (size_t)F_HX * F_HY * F_RS * sizeof(float) + (size_t)F_TILE * sizeof(int32_t);
+}
+
+struct SeedWeights {
+    float w[13];   // step weights of offsets k = 0..12 (== those of 26-k)
+    float c1;      // "clearly uphill" threshold on the score, relative to |rho_c|
+    float floor_;  // and its absolute floor (denormal densities go the exact way)
+    unsigned tag_mask;  // 0xfffffff0, passed in so the tagging stays one LOP3 per score
+};
+
+// float bits -> unsigned with the same order (negative densities included)
+__device__ __forceinline__ unsigned sortable_key(float f) {
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+
+// the exact fp64 step, kept out of line: it runs for a handful of voxels per tile
+__device__ __noinline__ int seed_exact_step(const double *__restrict__ rho, Grid g, const Weights &W,
+                                            int x, int y, int z) {
+    int t[3];
+    return ongrid_step_gmem(rho, g, W, x, y, z, t);
+}
+
+template <int PH, int ZO>
+__device__ __forceinline__ float seed_best(const float (&P)[3][12], const SeedWeights &Wf, float rc,
+                                           unsigned mask) {
+    constexpr int A = PH % 3, B = (PH + 1) % 3, C = (PH + 2) % 3;
+    float best = 0.f;
+#pragma unroll
+    for (int k = 0; k < 13; ++k) {
+        const int a = k / 9, b = (k / 3) % 3, c = k % 3;
+        const int pa = a == 0 ? A : (a == 1 ? B : C);
+        const int pb = a == 0 ? C : (a == 1 ? B : A);
+        const float m = fmaxf(P[pa][b * 4 + c + ZO], P[pb][(2 - b) * 4 + (2 - c) + ZO]);
+        float s = __fmul_rn(__fsub_rn(m, rc), Wf.w[k]);
+        unsigned tagged;  // (bits & mask) | k in one LOP3
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(tagged) : "r"(__float_as_uint(s)), "r"(mask), "r"(k));
+        best = fmaxf(best, __uint_as_float(tagged));  // NaN (both of a pair are vacuum) never wins
+    }
+    return best;
+}
+
+template <int VAC>
+__global__ void __launch_bounds__(256, 3)
+k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeights Wf, Weights W,
+                double vac_tol, unsigned long long *root_counter, int32_t *roots,
+                int64_t roots_cap, int exit_base, int x_begin, uint32_t *tile_keys) {
+    extern __shared__ float s_f[];  // [F_HX][F_HY][F_RS]: z0-1 at column 0, body 1..64, z0+64 at 65
+    int32_t *s_code = reinterpret_cast<int32_t *>(s_f + F_HX * F_HY * F_RS);
+    __shared__ TileIdx<1, FX, FY, FZ> idx;
+    __shared__ int s_off[13], s_dl[13];
+    __shared__ unsigned s_key;
+    const int x0 = x_begin + blockIdx.z * FX, y0 = blockIdx.y * FY, z0 = blockIdx.x * FZ;
+    tile_index_tables(idx, g, x0, y0, z0);
+    if (threadIdx.x < 13) {
+        const int k = threadIdx.x, a = k / 9, b = (k / 3) % 3, c = k % 3;
+        s_off[k] = ((a - 1) * F_HY + (b - 1)) * F_RS + (c - 1);  // in the fp32 tile
+        s_dl[k] = ((a - 1) * FY + (b - 1)) * FZ + (c - 1);       // in the code tile
+    }
+    if (threadIdx.x == 0) s_key = 0u;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // ---- stage the tile as fp32: one warp per (x,y) row, a lane per z pair ----
+        const bool vec = ((g.nz & 1) == 0) && (z0 + FZ <= g.nz);
+        const int zb0 = idx.zi[2 * lane + 1], zb1 = idx.zi[2 * lane + 2];
+        const int zh = idx.zi[lane == 0 ? 0 : FZ + 1];
+        const int ch = lane == 0 ? 0 : FZ + 1;
+        constexpr int NR = F_HX * F_HY, U = 6;
+        for (int r0 = warp; r0 < NR; r0 += 8 * U) {
+            double va[U], vb[U], vh[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + 8 * u;
+                if (r < NR) {
+                    const int lx = r / F_HY, ly = r - lx * F_HY;
+                    const double *row = rho + (idx.xi[lx] * g.ny + idx.yi[ly]) * g.nz;
+                    if (vec) {
+                        const double2 q = *reinterpret_cast<const double2 *>(row + zb0);
+                        va[u] = q.x;
+                        vb[u] = q.y;
+                    } else {
+                        va[u] = row[zb0];
+                        vb[u] = row[zb1];
+                    }
+                    if (lane < 2) vh[u] = row[zh];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + 8 * u;
+                if (r < NR) {
+                    float fa = __double2float_rn(va[u]), fb = __double2float_rn(vb[u]);
+                    if (VAC == VAC_TOL) {
+                        if (va[u] <= vac_tol) fa = -INFINITY;
+                        if (vb[u] <= vac_tol) fb = -INFINITY;
+                    }
+                    s_f[r * F_RS + 2 * lane + 1] = fa;
+                    s_f[r * F_RS + 2 * lane + 2] = fb;
+                    if (lane < 2) {
+                        float fh = __double2float_rn(vh[u]);
+                        if (VAC == VAC_TOL && vh[u] <= vac_tol) fh = -INFINITY;
+                        s_f[r * F_RS + ch] = fh;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int ty = warp, tz0 = 2 * lane;
+    const int gy = y0 + ty, gz0 = z0 + tz0;
+    const bool ok0 = gy < g.ny && gz0 < g.nz, ok1 = gy < g.ny && gz0 + 1 < g.nz;
+    // vacuum flags of the two columns up front (bit tx: voxel A, bit 16+tx: voxel B)
+    unsigned vac = 0;
+    if (VAC == VAC_LABELS) {
+#pragma unroll
+        for (int tx = 0; tx < FX; ++tx)
+            if (x0 + tx < g.nx) {
+                const int v = lin3(g, x0 + tx, gy, gz0);
+                if (ok0) vac |= (code[v] == -1 ? 1u : 0u) << tx;
+                if (ok1) vac |= (code[v + 1] == -1 ? 1u : 0u) << (16 + tx);
+            }
+    }
+    // which of the 9 (dy,dz) moves stay inside the tile and the grid, per voxel
+    unsigned ok_yz[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r9 = 0; r9 < 9; ++r9) {
+            const int uy = ty + r9 / 3 - 1, uz = tz0 + j + r9 % 3 - 1;
+            const bool ok = uy >= 0 && uy < FY && uz >= 0 && uz < FZ && y0 + uy < g.ny && z0 + uz < g.nz;
+            ok_yz[j] |= (ok ? 1u : 0u) << r9;
+        }
+
+    // P[p][r*4+j]: register plane p, row r (y-1..y+1), column j (z0-1 .. z0+2 of the pair)
+    float P[3][12];
+    const float *col = s_f + ty * F_RS + 2 * lane;
+    auto load_plane = [&](float (&Q)[12], int p) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float2 q0 = *reinterpret_cast<const float2 *>(col + (p * F_HY + r) * F_RS);
+            const float2 q1 = *reinterpret_cast<const float2 *>(col + (p * F_HY + r) * F_RS + 2);
+            Q[r * 4 + 0] = q0.x; Q[r * 4 + 1] = q0.y; Q[r * 4 + 2] = q1.x; Q[r * 4 + 3] = q1.y;
+        }
+    };
+    load_plane(P[0], 0);
+    load_plane(P[1], 1);
+    float colmax = -INFINITY;
+    unsigned mask;
+    asm volatile("mov.b32 %0, %1;" : "=r"(mask) : "r"(Wf.tag_mask));
+
+    // one voxel: turn the fp32 winner (or the exact fallback) into a pointer code
+    auto finish = [&](float best, float rc, int j, int tx, bool ok) {
+        const int tz = tz0 + j, gx = x0 + tx, gz = gz0 + j;
+        const int e = (tx * FY + ty) * FZ + tz;
+        int32_t cde = -1;
+        if (ok && gx < g.nx) {
+            const bool is_vac = VAC == VAC_LABELS ? ((vac >> (16 * j + tx)) & 1u) != 0
+                                                  : (VAC == VAC_TOL ? rc == -INFINITY : false);
+            const bool is_exit = exit_base > 0 && (gx == 0 || gx == g.nx - 1);
+            if (is_exit) {
+                cde = -2 - ((gx == 0 ? 0 : g.ny * g.nz) + gy * g.nz + gz);
+            } else if (!is_vac) {
+                colmax = fmaxf(colmax, rc);
+                const float thr = fmaxf(fabsf(rc) * Wf.c1, Wf.floor_);
+                if (best >= thr) {
+                    const int k = __float_as_int(best) & 15;
+                    const float *cp = col + ((tx + 1) * F_HY + 1) * F_RS + 1 + j;
+                    const int off = s_off[k];
+                    const bool lo = cp[off] >= cp[-off];
+                    const int bk = lo ? k : 26 - k;
+                    const unsigned lo9 = tx > 0 ? ok_yz[j] : 0u;
+                    const unsigned hi9 = (tx < FX - 1 && gx + 1 < g.nx) ? ok_yz[j] : 0u;
+                    const unsigned ok27 = lo9 | (ok_yz[j] << 9) | (hi9 << 18);
+                    if ((ok27 >> bk) & 1u) {
+                        cde = lo ? e + s_dl[k] : e - s_dl[k];
+                    } else {
+                        const int a = bk / 9, r9 = bk - 9 * a, b3 = r9 / 3, c3 = r9 - 3 * b3;
+                        cde = F_TILE + lin3(g, idx.xi[tx + a], idx.yi[ty + b3], idx.zi[tz + c3]);
+                    }
+                } else {
+                    // not clearly uphill in fp32: the reference's own step decides
+                    const int self = lin3(g, gx, gy, gz);
+                    const int tl = seed_exact_step(rho, g, W, gx, gy, gz);
+                    if (tl == self) {
+                        const unsigned long long s = atomicAdd(root_counter, 1ULL);
+                        if ((int64_t)s < roots_cap) roots[s] = self;
+                        cde = -2 - (exit_base + (int32_t)s);
+                    } else {
+                        cde = F_TILE + tl;
+                    }
+                }
+            }
+        }
+        s_code[e] = cde;
+    };
+
+#pragma unroll 1
+    for (int tx = 0; tx < FX; tx += 3) {
+        load_plane(P[2], tx + 2);
+        finish(seed_best<0, 0>(P, Wf, P[1][5], mask), P[1][5], 0, tx, ok0);
+        finish(seed_best<0, 1>(P, Wf, P[1][6], mask), P[1][6], 1, tx, ok1);
+        load_plane(P[0], tx + 3);
+        finish(seed_best<1, 0>(P, Wf, P[2][5], mask), P[2][5], 0, tx + 1, ok0);
+        finish(seed_best<1, 1>(P, Wf, P[2][6], mask), P[2][6], 1, tx + 1, ok1);
+        load_plane(P[1], tx + 4 < F_HX ? tx + 4 : F_HX - 1);
+        finish(seed_best<2, 0>(P, Wf, P[0][5], mask), P[0][5], 0, tx + 2, ok0);
+        finish(seed_best<2, 1>(P, Wf, P[0][6], mask), P[0][6], 1, tx + 2, ok1);
+    }
+    // tile key for the resolve order: the largest density of the tile
+    if (tile_keys) {
+        const unsigned km = __reduce_max_sync(0xffffffffu, sortable_key(colmax));
+        if (lane == 0) atomicMax(&s_key, km);
+    }
+    __syncthreads();
+    if (tile_keys && threadIdx.x == 0)
+        tile_keys[((x0 / FX) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s_key;
+    if (!ok0) return;
+    // chase every pointer inside the tile, then store the pair
+    const bool pair_store = ok1 && ((g.nz & 1) == 0);
+#pragma unroll 2
+    for (int tx = 0; tx < FX; ++tx) {
+        const int gx = x0 + tx;
+        if (gx >= g.nx) break;
+        const int e = (tx * FY + ty) * FZ + tz0;
+        int32_t c[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int32_t cc = s_code[e + j];
+            if (cc >= 0 && cc < F_TILE) {
+                do cc = s_code[cc];
+                while (cc >= 0 && cc < F_TILE);
+                s_code[e + j] = cc;  // path compression for the voxels that point here
+            }
+            c[j] = cc >= F_TILE ? cc - F_TILE : cc;
+        }
+        const int v = lin3(g, gx, gy, gz0);
+        if (pair_store) {
+            *reinterpret_cast<int2 *>(code + v) = make_int2(c[0], c[1]);
+        } else {
+            code[v] = c[0];
+            if (ok1) code[v + 1] = c[1];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------
+// K2  tile-ordered pointer resolution.
+//
+// After the stencil pass every voxel holds a terminal code or the index of
+// the voxel where its path enters another tile.  Tiles are visited in order of
+// decreasing largest density (16-bit counting sort of the keys the stencil
+// pass left behind): an ascent path only enters tiles that hold larger
+// densities, and those were resolved thousands of CTAs earlier, so almost
+// every chain is one hop long and the pass is one coalesced read, one gather
+// and one coalesced write per voxel instead of a ~10-hop chase.
+// Correctness does not depend on the order: a reader that meets an unresolved
+// pointer simply keeps following the (acyclic) chain.
+// Algorithmic traffic: R 4 + W 4 per voxel (+ the gathers, mostly L1/L2 hits).
+// -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tile_hist(const uint32_t *__restrict__ keys, int n, unsigned *hist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(hist + (65535u - (keys[i] >> 16)), 1u);
+}
+// exclusive scan of the 65536 bins by one CTA of 1024 threads
+__global__ void __launch_bounds__(1024)
+k_tile_scan(unsigned *hist) {
+    __shared__ unsigned s_part[1024];
+    const int t = threadIdx.x;
+    unsigned loc[64], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        loc[i] = hist[t * 64 + i];
+        sum += loc[i];
+    }
+    s_part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned u = t >= o ? s_part[t - o] : 0u;
+        __syncthreads();
+        s_part[t] += u;
+        __syncthreads();
+    }
+    unsigned run = s_part[t] - sum;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        hist[t * 64 + i] = run;
+        run += loc[i];
+    }
+}
+__global__ void __launch_bounds__(256)
+k_tile_scatter(const uint32_t *__restrict__ keys, int n, unsigned *offsets, int32_t *order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[atomicAdd(offsets + (65535u - (keys[i] >> 16)), 1u)] = i;
+}
+
+// one CTA per tile of TX x TY x TZ voxels (the stencil pass's tiling), in the
+// given order.  VEC: nz % 4 == 0, so the four voxels of a thread move as one
+// 16-byte access.
+template <int TX, int TY, int TZ, bool VEC>
+__global__ void __launch_bounds__(256)
+k_resolve_tiles(int32_t *code, Grid g, const int32_t *__restrict__ order, int tiles_z, int tiles_y,
+                int32_t *minidx) {
+    constexpr int QPR = TZ / 4;          // 16-byte groups per row
+    constexpr int ROWS = TX * TY;
+    constexpr int RPP = 256 / QPR;       // rows per pass of the CTA
+    constexpr int B = 3;                 // rows in flight per thread
+    const int tile = order[blockIdx.x];
+    const int bz = tile % tiles_z, by = (tile / tiles_z) % tiles_y, bx = tile / (tiles_z * tiles_y);
+    const int q = threadIdx.x % QPR, r_in = threadIdx.x / QPR;
+    const int z = bz * TZ + 4 * q;
+    if (z >= g.nz) return;
+    for (int rb = r_in; rb < ROWS; rb += RPP * B) {
+        int32_t c[B][4];
+        int v[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int r = rb + u * RPP;
+            const int lx = r / TY, ly = r - lx * TY;
+            const int x = bx * TX + lx, y = by * TY + ly;
+            v[u] = -1;
+            if (r < ROWS && x < g.nx && y < g.ny) {
+                v[u] = lin3(g, x, y, z);
+                if (VEC) {
+                    const int4 t = *reinterpret_cast<const int4 *>(code + v[u]);
+                    c[u][0] = t.x; c[u][1] = t.y; c[u][2] = t.z; c[u][3] = t.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) c[u][k] = z + k < g.nz ? code[v[u] + k] : -1;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) c[u][k] = -1;
+            }
+        }
+        // first hop of every chain together, then the (rare) rest
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c[u][k] >= 0) c[u][k] = __ldca(code + c[u][k]);
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                while (c[u][k] >= 0) c[u][k] = __ldcg(code + c[u][k]);
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            if (v[u] < 0) continue;
+            if (VEC) {
+                *reinterpret_cast<int4 *>(code + v[u]) = make_int4(c[u][0], c[u][1], c[u][2], c[u][3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (z + k < g.nz) code[v[u] + k] = c[u][k];
+            }
+            if (minidx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c[u][k] <= -2 && z + k < g.nz) {
+                        const int s = -2 - c[u][k];
+                        if (v[u] + k < minidx[s]) atomicMin(minidx + s, v[u] + k);
+                    }
+            }
+        }
+    }
+}
+
+}  // namespace bdr

@@ -151,10 +151,10 @@ class ShardedBader:
         if os.environ.get('BDR_DEBUG'):
             print(f"[sharded r{self.comm.rank}] {msg}", file=sys.stderr, flush=True)
 
-    def ongrid(self, dist_mat):
+    def ongrid(self, dist_mat, method='ongrid'):
         be, H, P = self.backend, self.halo, self.plane
         self._dbg("seed")
-        n_real, exit_base = be.seed(dist_mat)
+        n_real, exit_base = be.seed(dist_mat, method)
         self._dbg(f"seeded: {n_real} local maxima")
         codes = be.labels()                      # int32 [W, ny, nz]: -1 vacuum, -2-s slots
         dev = codes.device
@@ -262,7 +262,7 @@ class ShardedBader:
         `max_passes`; `self.settled` says whether the last one was quiet).
         A backend with `requeue` re-traces only the edges next to voxels that
         moved (like the single-GPU bader_calc); otherwise full passes."""
-        self.ongrid(dist_mat)
+        self.ongrid(dist_mat, 'neargrid')
         be = self.backend
         if not hasattr(be, 'requeue'):
             hist = self.refine(dist_mat, T_grad, max_passes)
@@ -397,8 +397,11 @@ class SlabBackend:
                                            device=self.device)
         return self._labels
 
-    def seed(self, dist_mat):
+    def seed(self, dist_mat, method='ongrid'):
         self._sync()
+        # BDR_OPT_SLAB_SEED_METHOD: 'neargrid' takes the fp32-ranked seed stencil,
+        # exactly as bdr_bader_calc does on one GPU
+        self.check(self.lib.bdr_set_option(self.h, 1, 1 if method == 'neargrid' else 0))
         d = np.ascontiguousarray(dist_mat, dtype=np.float64)
         n, xb = ctypes.c_int64(0), ctypes.c_int64(0)
         self.check(self.lib.bdr_slab_seed(self.h, d.ctypes.data, ctypes.byref(n), ctypes.byref(xb)))

@@ -48,7 +48,7 @@ class ModelBackend:
     def labels(self):
         return self._labels_t
 
-    def seed(self, dist_mat):
+    def seed(self, dist_mat, method='ongrid'):
         W = self.shape[0]
         ptr = ongrid_pointers(self.rho, np.asarray(dist_mat)).reshape(-1)
         lin = np.arange(self.N, dtype=np.int64)
