@@ -2,7 +2,9 @@
 // include/bader_b200.h on top of the kernels in kernels.cuh.
 #include "kernels.cuh"
 #include "seed.cuh"
+#include "edge.cuh"
 
+#include <chrono>
 #include <cstdlib>
 
 namespace bdr {
@@ -106,10 +108,13 @@ static int ensure_bits(bdr_ctx *c) {
     if (c->ebits) return 0;
     c->nzw = (c->g.nz + 31) / 32;
     const size_t words = (size_t)c->g.nx * c->g.ny * c->nzw;
-    CU(cudaMalloc((void **)&c->ebits, 4 * words * sizeof(uint32_t)));
+    CU(cudaMalloc((void **)&c->ebits, 7 * words * sizeof(uint32_t)));
     c->vbits = c->ebits + words;
     c->cbits = c->vbits + words;
     c->sbits = c->cbits + words;
+    c->eqz = c->sbits + words;
+    c->eqy = c->eqz + words;
+    c->eqx = c->eqy + words;
     return 0;
 }
 static int ensure_rho(bdr_ctx *c, int which) {
@@ -217,16 +222,17 @@ static int stencil_launch(bdr_ctx *c, const Weights &W_full, int x_begin, int x_
         SeedWeights Wf;
         seed_weights(W_full, &Wf);
         const size_t smem = seed_smem();
+        const double *W_dev = c->d_seedw;
         if (c->vac_mode == VAC_NONE)
             LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_NONE>), grid, 256, smem, rho, code, c->g, Wf,
-                   W_full, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin, c->tile_keys);
+                   W_dev, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin, c->tile_keys);
         else if (c->vac_mode == VAC_TOL)
             LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_TOL>), grid, 256, smem, rho, code, c->g, Wf,
-                   W_full, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
+                   W_dev, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
                    c->tile_keys);
         else
             LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_LABELS>), grid, 256, smem, rho, code, c->g,
-                   Wf, W_full, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
+                   Wf, W_dev, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
                    c->tile_keys);
         return 0;
     }
@@ -248,9 +254,15 @@ static int stencil_launch(bdr_ctx *c, const Weights &W_full, int x_begin, int x_
 
 // which stencil kernel seeds this call: the fp32-ranked one for 'neargrid'
 // (seed.cuh), the bit-exact fp64 one for 'ongrid'
-static void choose_seed(bdr_ctx *c, int method, const Weights &W) {
+static int choose_seed(bdr_ctx *c, int method, const Weights &W) {
     SeedWeights Wf;
     c->seed_f32 = method == BDR_METHOD_NEARGRID && seed_weights(W, &Wf) && !getenv("BDR_SEED_EXACT");
+    if (c->seed_f32) {
+        // the exact fallback of the seed kernel reads the fp64 weights from global memory
+        if (!c->d_seedw) CU(cudaMalloc((void **)&c->d_seedw, sizeof(Weights)));
+        CU(cudaMemcpyAsync(c->d_seedw, W.w, sizeof(Weights), cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
 }
 
 // pointer codes -> terminal codes, tile by tile in order of decreasing density
@@ -334,6 +346,7 @@ static int upload_and_stencil_dev(bdr_ctx *c, const double *host, const Weights 
     const int64_t plane = (int64_t)c->g.ny * c->g.nz;
     double *rho = c->rho[BDR_RHO_REFERENCE];
     CU(cudaStreamSynchronize(c->stream));  // nothing may still read the old density
+    const auto t_up = std::chrono::steady_clock::now();
     for (int i = 0; i < nchunks; ++i) {
         const int xa = i * CH, xe = std::min(c->g.nx, xa + CH);
         CU(cudaMemcpyAsync(rho + xa * plane, host + xa * plane, (size_t)(xe - xa) * plane * sizeof(double),
@@ -349,6 +362,7 @@ static int upload_and_stencil_dev(bdr_ctx *c, const double *host, const Weights 
     CU(cudaStreamWaitEvent(c->stream, c->chunk_events[(size_t)nchunks - 1], 0));
     TRY(stencil_launch(c, W, 0, std::min(c->g.nx, CH)));
     TRY(read_counters(c));
+    c->dbg_upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count();
     int64_t n = (int64_t)c->h_cnt[CNT_ROOTS];
     if (n > c->slots_cap) {  // more maxima than slots: redo on the resident density
         TRY(ensure_slots(c, n));
@@ -413,35 +427,58 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
     TRY(ensure_bits(c));
     if (!c->labels[which]) return fail_msg("edge_find: label set is empty");
     TRY(ensure(&c->list, &c->list_cap, std::max<int64_t>(c->N / 16, 1024)));
-    const dim3 grid((c->g.nz + 127) / 128, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
-    if ((c->g.nz & 3) == 0)
-        LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_bits<EDGE_CX, true>), grid, 256, 0, c->labels[which], c->g,
-               c->ebits, c->vbits, c->nzw);
-    else
-        LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_bits<EDGE_CX, false>), grid, 256, 0, c->labels[which], c->g,
-               c->ebits, c->vbits, c->nzw);
-    // masked pass (n_changed >= 0): list only the edges in the 27-neighbourhood
-    // of the voxels in c->list2 (the ones the last trace relabelled)
-    const uint32_t *mask = nullptr;
-    if (n_changed >= 0) {
-        const size_t words = (size_t)c->g.nx * c->g.ny * c->nzw;
-        CU(cudaMemsetAsync(c->cbits, 0, words * sizeof(uint32_t), c->stream));
-        if (n_changed > 0)
-            LAUNCH(c, BDR_K_EDGE_CHECK, k_bits_from_list, blocks_for(n_changed, 256), 256, 0, c->cbits,
-                   c->g, c->nzw, c->list2, n_changed);
-        mask = c->cbits;
-    }
+    const bool old_bits = getenv("BDR_EDGE_OLD") != nullptr;
+    if (!old_bits) TRY(ensure(&c->defer, &c->defer_cap, std::max<int64_t>(c->N / 64, 4096)));
     int64_t n = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        TRY(zero_counter(c, CNT_EDGES));
-        LAUNCH(c, BDR_K_EDGE_DILATE, k_edge_known,
-               dim3((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + 7) / 8), 256, 0, c->ebits, c->vbits,
-               c->known, c->g, c->nzw, c->d_cnt + CNT_EDGES, c->list, c->list_cap, mask, c->sbits,
-               sticky_mode);
-        TRY(read_counters(c));
-        n = (int64_t)c->h_cnt[CNT_EDGES];
-        if (n <= c->list_cap) break;
-        TRY(ensure(&c->list, &c->list_cap, n));  // the list overflowed: grow it and redo the cheap half
+    for (int pass = 0;; ++pass) {
+        if (old_bits) {
+            const dim3 grid((c->g.nz + 127) / 128, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
+            if ((c->g.nz & 3) == 0)
+                LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_bits<EDGE_CX, true>), grid, 256, 0, c->labels[which],
+                       c->g, c->ebits, c->vbits, c->nzw);
+            else
+                LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_bits<EDGE_CX, false>), grid, 256, 0, c->labels[which],
+                       c->g, c->ebits, c->vbits, c->nzw);
+        } else {
+            // label equality bits -> candidate bits (edge.cuh); voxels next to vacuum
+            // are classified exactly from a list (checked for overflow below)
+            CU(cudaMemsetAsync(c->d_cnt + CNT_DEFER, 0, 2 * sizeof(unsigned long long), c->stream));
+            const dim3 ga((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
+            LAUNCH(c, BDR_K_EDGE_FLAG, (k_label_eq_bits<4, EDGE_CX>), ga, 256, 0, c->labels[which], c->g,
+                   c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->d_cnt + CNT_VACSEEN);
+            const dim3 gb((c->g.ny * c->nzw + 255) / 256, (c->g.nx + 15) / 16);
+            LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_from_eq<16>), gb, 256, 0, c->eqz, c->eqy, c->eqx, c->vbits, c->g,
+                   c->nzw, c->ebits, c->d_cnt + CNT_VACSEEN, c->d_cnt + CNT_DEFER, c->defer,
+                   c->defer_cap);
+            LAUNCH(c, BDR_K_EDGE_FLAG, k_edge_deferred, 148 * 8, 128, 0, c->labels[which], c->g, c->nzw,
+                   c->ebits, c->defer, c->d_cnt + CNT_DEFER, c->defer_cap);
+        }
+        // masked pass (n_changed >= 0): list only the edges in the 27-neighbourhood
+        // of the voxels in c->list2 (the ones the last trace relabelled)
+        const uint32_t *mask = nullptr;
+        if (n_changed >= 0) {
+            const size_t words = (size_t)c->g.nx * c->g.ny * c->nzw;
+            CU(cudaMemsetAsync(c->cbits, 0, words * sizeof(uint32_t), c->stream));
+            if (n_changed > 0)
+                LAUNCH(c, BDR_K_EDGE_CHECK, k_bits_from_list, blocks_for(n_changed, 256), 256, 0, c->cbits,
+                       c->g, c->nzw, c->list2, n_changed);
+            mask = c->cbits;
+        }
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            TRY(zero_counter(c, CNT_EDGES));
+            LAUNCH(c, BDR_K_EDGE_DILATE, k_edge_known,
+                   dim3((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + 7) / 8), 256, 0, c->ebits, c->vbits,
+                   c->known, c->g, c->nzw, c->d_cnt + CNT_EDGES, c->list, c->list_cap, mask, c->sbits,
+                   sticky_mode);
+            TRY(read_counters(c));
+            n = (int64_t)c->h_cnt[CNT_EDGES];
+            if (n <= c->list_cap) break;
+            TRY(ensure(&c->list, &c->list_cap, n));  // the list overflowed: grow it and redo the cheap half
+        }
+        const int64_t nd = old_bits ? 0 : (int64_t)c->h_cnt[CNT_DEFER];
+        if (nd <= c->defer_cap) break;
+        if (pass == 1) return fail_msg("edge_find: deferred list overflow");
+        TRY(ensure(&c->defer, &c->defer_cap, nd));  // redo the pass with room for every deferred voxel
     }
     c->list_n = n;  // every candidate of the window; the trace kernel skips what it does not own
     *edges = 0;
@@ -938,7 +975,7 @@ int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *
     if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_slab_seed: density not set");
     const Weights W = make_weights(dist_mat);
     int64_t n = 0;
-    choose_seed(c, c->slab_seed_method, W);
+    TRY(choose_seed(c, c->slab_seed_method, W));
     TRY(stencil_dev(c, W, &n));
     TRY(resolve_dev(c, nullptr));
     CU(cudaStreamSynchronize(c->stream));
@@ -1071,7 +1108,8 @@ int bdr_destroy(bdr_ctx *c) {
     for (void *p : {(void *)c->known, (void *)c->list, (void *)c->list2, (void *)c->list3,
                     (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
                     (void *)c->d_sums, c->stage, (void *)c->ebits, (void *)c->term,
-                    (void *)c->tile_keys, (void *)c->tile_order, (void *)c->tile_hist})
+                    (void *)c->tile_keys, (void *)c->tile_order, (void *)c->tile_hist,
+                    (void *)c->d_seedw, (void *)c->defer})
         if (p) cudaFree(p);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -1214,7 +1252,7 @@ static int bader_calc_dev(bdr_ctx *c, int method, const double *dist_mat, const 
         return fail_msg("bdr_bader_calc: unknown method");
     if (method == BDR_METHOD_NEARGRID && !T_grad) return fail_msg("bdr_bader_calc: T_grad is null");
     const Weights W = make_weights(dist_mat);
-    choose_seed(c, method, W);
+    TRY(choose_seed(c, method, W));
     int64_t seeded = -1;
     if (host_density) TRY(upload_and_stencil_dev(c, host_density, W, &seeded));
     if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_bader_calc: reference density not uploaded");
@@ -1382,12 +1420,18 @@ int bdr_run(bdr_ctx *c, const double *host_density, double vac_tol, double voxel
     c->vac_mode = (vac_tol == vac_tol) ? VAC_TOL : VAC_NONE;
     c->vac_tol = vac_tol;
     int64_t n = 0;
+    const bool dbg = getenv("BDR_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(
+                        std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     TRY(bader_calc_dev(c, method, dist_mat, T_grad, &n, host_density));
+    const double t1 = now();
     if (refine_iters != 0) {
         int64_t run = 0;
         TRY(bdr_refine(c, BDR_LABELS_BADER, refine_mode, refine_iters, dist_mat, T_grad, &run,
                        nullptr, 0));
     }
+    const double t2 = now();
     if (n_maxima) *n_maxima = n;
     if (maxima) TRY(bdr_get_maxima(c, maxima, max_cap));
     if (charge || volume) {
@@ -1398,6 +1442,9 @@ int bdr_run(bdr_ctx *c, const double *host_density, double vac_tol, double voxel
         TRY(charge_sum_dev(c, BDR_LABELS_BADER, BDR_RHO_REFERENCE, voxel_volume, n, charge, volume));
     }
     if (host_labels) TRY(bdr_download_labels(c, BDR_LABELS_BADER, host_labels, label_elem_size));
+    if (dbg)
+        fprintf(stderr, "[bdr] run: upload+bader_calc %.1f ms (upload+stencil %.1f), refine %.1f ms, sums+download %.1f ms\n",
+                t1 - t0, c->dbg_upload_ms, t2 - t1, now() - t2);
     return 0;
 }
 

@@ -70,6 +70,8 @@ enum {
     CNT_VACUUM = 9,    // vacuum voxel count
     CNT_ESCAPED = 11,  // trajectories that left the trusted planes of a slab window
     CNT_STEPS = 10,    // trajectory steps taken by the trace kernel (accounting)
+    CNT_DEFER = 12,    // edge pass: voxels next to vacuum, classified from a list (edge.cuh)
+    CNT_VACSEEN = 13,  // edge pass: nonzero when the label volume holds vacuum voxels
     CNT_NUM = 16
 };
 
@@ -103,6 +105,9 @@ struct bdr_ctx {
     uint32_t *vbits = nullptr;  // vacuum bits, same layout (second half of the ebits allocation)
     uint32_t *cbits = nullptr;  // scratch bit volume (voxels relabelled by the last trace)
     uint32_t *sbits = nullptr;  // sticky "was ever an edge or next to one" bits (conservative passes)
+    uint32_t *eqz = nullptr, *eqy = nullptr, *eqx = nullptr;  // label equality bits (edge.cuh)
+    int32_t *defer = nullptr;   // edge pass: voxels next to vacuum
+    int64_t defer_cap = 0;
     int32_t *term = nullptr;    // where each traced voxel's trajectory ended (bader_calc('neargrid') only)
     bool use_term = false;
     int64_t last_changed = 0;   // entries of list2 written by the last trace (slab rounds)
@@ -125,6 +130,7 @@ struct bdr_ctx {
     uint32_t *tile_keys = nullptr; // largest density of every stencil tile (resolve order)
     int32_t *tile_order = nullptr;
     unsigned *tile_hist = nullptr;
+    double *d_seedw = nullptr;     // fp64 step weights for the seed kernel's exact fallback
     int64_t tiles_cap = 0;
     std::vector<int64_t> maxima;  // [n][3], in volume-number order
     int64_t n_max = 0;
@@ -151,6 +157,7 @@ struct bdr_ctx {
     int64_t launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int64_t trace_steps = 0, trace_voxels = 0;
+    double dbg_upload_ms = 0;  // BDR_DEBUG: host->device upload + stencil of the last bdr_run
 };
 
 namespace bdr {

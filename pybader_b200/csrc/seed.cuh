@@ -29,7 +29,7 @@
 
 namespace bdr {
 
-constexpr int FX = 12, FY = 8, FZ = 64;  // seed tile: 256 threads x (2 z voxels) x 12 planes
+constexpr int FX = 9, FY = 8, FZ = 64;  // seed tile: 256 threads x (2 z voxels) x 12 planes
 constexpr int F_HX = FX + 2, F_HY = FY + 2, F_RS = 68, F_TILE = FX * FY * FZ;
 constexpr size_t seed_smem() {
     return (size_t)F_HX * F_HY * F_RS * sizeof(float) + (size_t)F_TILE * sizeof(int32_t);
@@ -48,11 +48,33 @@ __device__ __forceinline__ unsigned sortable_key(float f) {
     return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
 }
 
-// the exact fp64 step, kept out of line: it runs for a handful of voxels per tile
-__device__ __noinline__ int seed_exact_step(const double *__restrict__ rho, Grid g, const Weights &W,
-                                            int x, int y, int z) {
-    int t[3];
-    return ongrid_step_gmem(rho, g, W, x, y, z, t);
+// the exact fp64 step (methods.py:87-117), kept out of line: it runs for a
+// handful of voxels per tile; the 27 step weights come from global memory
+__device__ __noinline__ int seed_exact_step(const double *__restrict__ rho, Grid g,
+                                            const double *__restrict__ w, int x, int y, int z) {
+    const int self = lin3(g, x, y, z);
+    const double rc = rho[self];
+    double best = rc;
+    int bi = self;
+#pragma unroll 1
+    for (int ix = -1; ix <= 1; ++ix) {
+        const int tx = wrap1(x + ix, g.nx);
+#pragma unroll 1
+        for (int iy = -1; iy <= 1; ++iy) {
+            const int ty = wrap1(y + iy, g.ny);
+#pragma unroll
+            for (int iz = -1; iz <= 1; ++iz) {
+                const int q = lin3(g, tx, ty, wrap1(z + iz, g.nz));
+                const double v = __dadd_rn(
+                    __dmul_rn(__dsub_rn(rho[q], rc), w[(ix + 1) * 9 + (iy + 1) * 3 + (iz + 1)]), rc);
+                if (v > best) {
+                    best = v;
+                    bi = q;
+                }
+            }
+        }
+    }
+    return bi;
 }
 
 template <int PH, int ZO>
@@ -75,8 +97,9 @@ __device__ __forceinline__ float seed_best(const float (&P)[3][12], const SeedWe
 }
 
 template <int VAC>
-__global__ void __launch_bounds__(256, 3)
-k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeights Wf, Weights W,
+__global__ void __launch_bounds__(256, 4)
+k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeights Wf,
+                const double *__restrict__ W,
                 double vac_tol, unsigned long long *root_counter, int32_t *roots,
                 int64_t roots_cap, int exit_base, int x_begin, uint32_t *tile_keys) {
     extern __shared__ float s_f[];  // [F_HX][F_HY][F_RS]: z0-1 at column 0, body 1..64, z0+64 at 65
