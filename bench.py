@@ -42,7 +42,7 @@ SHAPES = {1: (1024, 1024, 1024), 2: (2048, 1024, 1024), 4: (2048, 2048, 1024),
           8: (2048, 2048, 2048)}
 
 # algorithmic bytes per voxel of each streaming kernel family
-ALG_BYTES = {'stencil': 12, 'resolve': 8, 'relabel': 8, 'edge_flag': 4.25, 'edge_dilate': 1.25,
+ALG_BYTES = {'stencil': 12, 'resolve': 8, 'relabel': 8, 'edge_flag': 5.125, 'edge_dilate': 1.25,
              'first': 4, 'charge_sum': 12, 'vacuum': 12, 'narrow': 5}
 
 
@@ -194,6 +194,38 @@ def workload_name(shape):
             f"refine('changed',2)")
 
 
+# kernel names behind each family (for the DRAM traffic measured by ncu, profiles/*_traffic.json)
+FAMILY_KERNELS = {'trace': ['k_trace'], 'stencil': ['k_seed_pointers', 'k_ongrid_pointers'],
+                  'resolve': ['k_resolve_tiles', 'k_tile_hist', 'k_tile_scan', 'k_tile_scatter'],
+                  'edge_flag': ['k_label_eq_bits', 'k_edge_from_eq', 'k_edge_deferred'],
+                  'edge_dilate': ['k_edge_known'], 'relabel': ['k_relabel_slots'],
+                  'first': ['k_first_voxel_slots'], 'edge_confirm': ['k_edge_confirm']}
+
+
+def measured_traffic(family, n_voxels):
+    """DRAM bytes per launch of a kernel family from the committed ncu capture of one
+    step of this workload (dram__bytes_read.sum + dram__bytes_write.sum), or None"""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+        except (OSError, ValueError):
+            continue
+        if d.get('voxels') != n_voxels:
+            continue
+        tot, n = 0.0, 0
+        for k in FAMILY_KERNELS.get(family, []):
+            e = d['kernels'].get(k)
+            if e:
+                tot += e['dram_read_bytes'] + e['dram_write_bytes']
+                n += e['launches']
+        if n:
+            return {"bytes_per_launch": tot / n, "launches_captured": n,
+                    "source": 'profiles/' + os.path.basename(path)}
+    return None
+
+
 def kernel_accounting(prof, n_voxels, steps, tsteps, tvox, ms_per_step):
     """per-family table (CUDA-event times on the library's stream) and the roofline
     object of the family that takes the largest share of the step; n_voxels is what
@@ -219,8 +251,11 @@ def kernel_accounting(prof, n_voxels, steps, tsteps, tvox, ms_per_step):
     dom = max((k for k in kernels if 'achieved_gbs' in kernels[k]),
               key=lambda k: kernels[k]['ms_per_step'])
     dk = kernels[dom]
+    tr = measured_traffic(dom, n_voxels)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": dk['achieved_gbs'], "peak": peak,
-                "unit": "GB/s", "frac": dk['achieved_gbs'] / peak, "traffic": None,
+                "unit": "GB/s", "frac": dk['achieved_gbs'] / peak,
+                "traffic": tr and tr['bytes_per_launch'], "traffic_source": tr and tr['source'],
+                "alg_bytes_per_launch": dk['achieved_gbs'] * 1e9 * dk['ms_per_step'] / dk['launches_per_step'] * 1e-3,
                 "peak_source": peak_src, "ms_per_launch": dk['ms_per_step'] / dk['launches_per_step'],
                 "share_of_step": dk['ms_per_step'] / ms_per_step}
     return kernels, roofline

@@ -223,17 +223,16 @@ static int stencil_launch(bdr_ctx *c, const Weights &W_full, int x_begin, int x_
         seed_weights(W_full, &Wf);
         const size_t smem = seed_smem();
         const double *W_dev = c->d_seedw;
-        if (c->vac_mode == VAC_NONE)
-            LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_NONE>), grid, 256, smem, rho, code, c->g, Wf,
-                   W_dev, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin, c->tile_keys);
-        else if (c->vac_mode == VAC_TOL)
-            LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_TOL>), grid, 256, smem, rho, code, c->g, Wf,
-                   W_dev, c->vac_tol, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
-                   c->tile_keys);
-        else
-            LAUNCH(c, BDR_K_STENCIL, (k_seed_pointers<VAC_LABELS>), grid, 256, smem, rho, code, c->g,
-                   Wf, W_dev, 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap, xb, x_begin,
-                   c->tile_keys);
+        using SeedKernel = void (*)(const double *, int32_t *, Grid, SeedWeights, const double *, double,
+                                    unsigned long long *, int32_t *, int64_t, int, int, uint32_t *);
+        const SeedKernel table[3][2] = {
+            {k_seed_pointers<VAC_NONE, false>, k_seed_pointers<VAC_NONE, true>},
+            {k_seed_pointers<VAC_TOL, false>, k_seed_pointers<VAC_TOL, true>},
+            {k_seed_pointers<VAC_LABELS, false>, k_seed_pointers<VAC_LABELS, true>}};
+        const SeedKernel kern = table[c->vac_mode][xb > 0 ? 1 : 0];
+        LAUNCH(c, BDR_K_STENCIL, kern, grid, 256, smem, rho, code, c->g, Wf, W_dev,
+               c->vac_mode == VAC_TOL ? c->vac_tol : 0.0, c->d_cnt + CNT_ROOTS, c->roots, c->slots_cap,
+               xb, x_begin, c->tile_keys);
         return 0;
     }
     const HalfWeights W = half_weights(W_full);
@@ -893,12 +892,12 @@ int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out) {
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
     CU(cudaFuncSetAttribute(k_ongrid_pointers<SX, TY, TZ, VAC_LABELS>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil_smem()));
-    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)seed_smem()));
-    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_TOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)seed_smem()));
-    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_LABELS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_TOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_LABELS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_TOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem()));
+    CU(cudaFuncSetAttribute(k_seed_pointers<VAC_LABELS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem()));
     *out = c;
     return 0;
 }

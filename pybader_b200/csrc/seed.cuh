@@ -29,7 +29,7 @@
 
 namespace bdr {
 
-constexpr int FX = 9, FY = 8, FZ = 64;  // seed tile: 256 threads x (2 z voxels) x 12 planes
+constexpr int FX = 12, FY = 8, FZ = 64;  // seed tile: 256 threads x (2 z voxels) x 12 planes
 constexpr int F_HX = FX + 2, F_HY = FY + 2, F_RS = 68, F_TILE = FX * FY * FZ;
 constexpr size_t seed_smem() {
     return (size_t)F_HX * F_HY * F_RS * sizeof(float) + (size_t)F_TILE * sizeof(int32_t);
@@ -96,8 +96,15 @@ __device__ __forceinline__ float seed_best(const float (&P)[3][12], const SeedWe
     return best;
 }
 
-template <int VAC>
-__global__ void __launch_bounds__(256, 4)
+// Codes in the shared-memory tile are byte offsets while they point inside the
+// tile (4 * tile index), so one hop of the in-tile chase is LDS + compare:
+//     0 <= c < 4*F_TILE   pointer to the tile voxel at byte offset c
+//     c >= 4*F_TILE       4*F_TILE + global index of a voxel outside the tile
+//     c < 0               terminal (vacuum / maximum slot / exit slot)
+constexpr int F_T4 = 4 * F_TILE;
+
+template <int VAC, bool SLAB>
+__global__ void __launch_bounds__(256, 3)
 k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeights Wf,
                 const double *__restrict__ W,
                 double vac_tol, unsigned long long *root_counter, int32_t *roots,
@@ -105,69 +112,77 @@ k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeigh
     extern __shared__ float s_f[];  // [F_HX][F_HY][F_RS]: z0-1 at column 0, body 1..64, z0+64 at 65
     int32_t *s_code = reinterpret_cast<int32_t *>(s_f + F_HX * F_HY * F_RS);
     __shared__ TileIdx<1, FX, FY, FZ> idx;
-    __shared__ int s_off[13], s_dl[13];
+    __shared__ int s_off[13];   // fp32-tile offset of neighbour k (k < 13; 26-k is the negative)
+    __shared__ int s_t27[27];   // per move: code-tile byte delta << 8 | a | b << 2 | c << 4
     __shared__ unsigned s_key;
     const int x0 = x_begin + blockIdx.z * FX, y0 = blockIdx.y * FY, z0 = blockIdx.x * FZ;
     tile_index_tables(idx, g, x0, y0, z0);
-    if (threadIdx.x < 13) {
+    if (threadIdx.x < 27) {
         const int k = threadIdx.x, a = k / 9, b = (k / 3) % 3, c = k % 3;
-        s_off[k] = ((a - 1) * F_HY + (b - 1)) * F_RS + (c - 1);  // in the fp32 tile
-        s_dl[k] = ((a - 1) * FY + (b - 1)) * FZ + (c - 1);       // in the code tile
+        if (k < 13) s_off[k] = ((a - 1) * F_HY + (b - 1)) * F_RS + (c - 1);
+        const int dl = 4 * (((a - 1) * FY + (b - 1)) * FZ + (c - 1));
+        s_t27[k] = dl * 256 + (a | (b << 2) | (c << 4));
     }
     if (threadIdx.x == 0) s_key = 0u;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {   // ---- stage the tile as fp32: one warp per (x,y) row, a lane per z pair ----
+    const int plane = g.ny * g.nz;
+    {   // ---- stage the tile as fp32: a warp per (x,y) row, a lane per z pair; warp w
+        // takes row y = w of every x plane, the two halo rows y = 8, 9 are dealt round ----
         const bool vec = ((g.nz & 1) == 0) && (z0 + FZ <= g.nz);
         const int zb0 = idx.zi[2 * lane + 1], zb1 = idx.zi[2 * lane + 2];
         const int zh = idx.zi[lane == 0 ? 0 : FZ + 1];
         const int ch = lane == 0 ? 0 : FZ + 1;
-        constexpr int NR = F_HX * F_HY, U = 6;
-        for (int r0 = warp; r0 < NR; r0 += 8 * U) {
-            double va[U], vb[U], vh[U];
+        auto rows = [&](auto lx_of, auto ly_of, int count) {
+            constexpr int U = 7;
+            for (int i0 = 0; i0 < count; i0 += U) {
+                double va[U], vb[U], vh[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int r = r0 + 8 * u;
-                if (r < NR) {
-                    const int lx = r / F_HY, ly = r - lx * F_HY;
-                    const double *row = rho + (idx.xi[lx] * g.ny + idx.yi[ly]) * g.nz;
-                    if (vec) {
-                        const double2 q = *reinterpret_cast<const double2 *>(row + zb0);
-                        va[u] = q.x;
-                        vb[u] = q.y;
-                    } else {
-                        va[u] = row[zb0];
-                        vb[u] = row[zb1];
+                for (int u = 0; u < U; ++u)
+                    if (i0 + u < count) {
+                        const double *row = rho + (idx.xi[lx_of(i0 + u)] * plane + idx.yi[ly_of(i0 + u)] * g.nz);
+                        if (vec) {
+                            const double2 q = *reinterpret_cast<const double2 *>(row + zb0);
+                            va[u] = q.x;
+                            vb[u] = q.y;
+                        } else {
+                            va[u] = row[zb0];
+                            vb[u] = row[zb1];
+                        }
+                        if (lane < 2) vh[u] = row[zh];
                     }
-                    if (lane < 2) vh[u] = row[zh];
-                }
-            }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int r = r0 + 8 * u;
-                if (r < NR) {
-                    float fa = __double2float_rn(va[u]), fb = __double2float_rn(vb[u]);
-                    if (VAC == VAC_TOL) {
-                        if (va[u] <= vac_tol) fa = -INFINITY;
-                        if (vb[u] <= vac_tol) fb = -INFINITY;
+                for (int u = 0; u < U; ++u)
+                    if (i0 + u < count) {
+                        float *dst = s_f + (lx_of(i0 + u) * F_HY + ly_of(i0 + u)) * F_RS;
+                        float fa = __double2float_rn(va[u]), fb = __double2float_rn(vb[u]);
+                        if (VAC == VAC_TOL) {
+                            if (va[u] <= vac_tol) fa = -INFINITY;
+                            if (vb[u] <= vac_tol) fb = -INFINITY;
+                        }
+                        dst[2 * lane + 1] = fa;
+                        dst[2 * lane + 2] = fb;
+                        if (lane < 2) {
+                            float fh = __double2float_rn(vh[u]);
+                            if (VAC == VAC_TOL && vh[u] <= vac_tol) fh = -INFINITY;
+                            dst[ch] = fh;
+                        }
                     }
-                    s_f[r * F_RS + 2 * lane + 1] = fa;
-                    s_f[r * F_RS + 2 * lane + 2] = fb;
-                    if (lane < 2) {
-                        float fh = __double2float_rn(vh[u]);
-                        if (VAC == VAC_TOL && vh[u] <= vac_tol) fh = -INFINITY;
-                        s_f[r * F_RS + ch] = fh;
-                    }
-                }
             }
-        }
+        };
+        rows([](int i) { return i; }, [&](int) { return warp; }, F_HX);
+        // 28 halo rows (x plane e >> 1, y row 8 + (e & 1)), e = warp, warp + 8, ...
+        rows([&](int i) { return (warp + 8 * i) >> 1; }, [&](int i) { return 8 + ((warp + 8 * i) & 1); },
+             (2 * F_HX - warp + 7) / 8);
     }
     __syncthreads();
 
     const int ty = warp, tz0 = 2 * lane;
     const int gy = y0 + ty, gz0 = z0 + tz0;
     const bool ok0 = gy < g.ny && gz0 < g.nz, ok1 = gy < g.ny && gz0 + 1 < g.nz;
+    // extent of the tile inside the grid: a move stays in the tile iff it stays below these
+    const unsigned ex = min(FX, g.nx - x0), ey = min(FY, g.ny - y0), ez = min(FZ, g.nz - z0);
     // vacuum flags of the two columns up front (bit tx: voxel A, bit 16+tx: voxel B)
     unsigned vac = 0;
     if (VAC == VAC_LABELS) {
@@ -179,16 +194,6 @@ k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeigh
                 if (ok1) vac |= (code[v + 1] == -1 ? 1u : 0u) << (16 + tx);
             }
     }
-    // which of the 9 (dy,dz) moves stay inside the tile and the grid, per voxel
-    unsigned ok_yz[2] = {0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int r9 = 0; r9 < 9; ++r9) {
-            const int uy = ty + r9 / 3 - 1, uz = tz0 + j + r9 % 3 - 1;
-            const bool ok = uy >= 0 && uy < FY && uz >= 0 && uz < FZ && y0 + uy < g.ny && z0 + uz < g.nz;
-            ok_yz[j] |= (ok ? 1u : 0u) << r9;
-        }
 
     // P[p][r*4+j]: register plane p, row r (y-1..y+1), column j (z0-1 .. z0+2 of the pair)
     float P[3][12];
@@ -206,18 +211,19 @@ k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeigh
     float colmax = -INFINITY;
     unsigned mask;
     asm volatile("mov.b32 %0, %1;" : "=r"(mask) : "r"(Wf.tag_mask));
+    const int eb0 = 4 * (ty * FZ + tz0);  // byte offset of voxel A of plane 0 in the code tile
 
     // one voxel: turn the fp32 winner (or the exact fallback) into a pointer code
     auto finish = [&](float best, float rc, int j, int tx, bool ok) {
-        const int tz = tz0 + j, gx = x0 + tx, gz = gz0 + j;
-        const int e = (tx * FY + ty) * FZ + tz;
+        const int tz = tz0 + j, gx = x0 + tx;
+        const int eb = eb0 + 4 * j + tx * (4 * FY * FZ);
         int32_t cde = -1;
         if (ok && gx < g.nx) {
             const bool is_vac = VAC == VAC_LABELS ? ((vac >> (16 * j + tx)) & 1u) != 0
                                                   : (VAC == VAC_TOL ? rc == -INFINITY : false);
-            const bool is_exit = exit_base > 0 && (gx == 0 || gx == g.nx - 1);
+            const bool is_exit = SLAB && (gx == 0 || gx == g.nx - 1);
             if (is_exit) {
-                cde = -2 - ((gx == 0 ? 0 : g.ny * g.nz) + gy * g.nz + gz);
+                cde = -2 - ((gx == 0 ? 0 : plane) + gy * g.nz + gz0 + j);
             } else if (!is_vac) {
                 colmax = fmaxf(colmax, rc);
                 const float thr = fmaxf(fabsf(rc) * Wf.c1, Wf.floor_);
@@ -225,32 +231,30 @@ k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeigh
                     const int k = __float_as_int(best) & 15;
                     const float *cp = col + ((tx + 1) * F_HY + 1) * F_RS + 1 + j;
                     const int off = s_off[k];
-                    const bool lo = cp[off] >= cp[-off];
-                    const int bk = lo ? k : 26 - k;
-                    const unsigned lo9 = tx > 0 ? ok_yz[j] : 0u;
-                    const unsigned hi9 = (tx < FX - 1 && gx + 1 < g.nx) ? ok_yz[j] : 0u;
-                    const unsigned ok27 = lo9 | (ok_yz[j] << 9) | (hi9 << 18);
-                    if ((ok27 >> bk) & 1u) {
-                        cde = lo ? e + s_dl[k] : e - s_dl[k];
-                    } else {
-                        const int a = bk / 9, r9 = bk - 9 * a, b3 = r9 / 3, c3 = r9 - 3 * b3;
-                        cde = F_TILE + lin3(g, idx.xi[tx + a], idx.yi[ty + b3], idx.zi[tz + c3]);
-                    }
+                    const int bk = cp[off] >= cp[-off] ? k : 26 - k;
+                    const int t = s_t27[bk];
+                    const unsigned a = t & 3, b = (t >> 2) & 3, c = (t >> 4) & 3;
+                    // tile coordinates of the target, -1 .. extent (as unsigned: -1 is huge)
+                    if (a + (unsigned)(tx - 1) < ex && b + (unsigned)(ty - 1) < ey &&
+                        c + (unsigned)(tz - 1) < ez)
+                        cde = eb + (t >> 8);
+                    else
+                        cde = F_T4 + lin3(g, idx.xi[tx + a], idx.yi[ty + b], idx.zi[tz + c]);
                 } else {
                     // not clearly uphill in fp32: the reference's own step decides
-                    const int self = lin3(g, gx, gy, gz);
-                    const int tl = seed_exact_step(rho, g, W, gx, gy, gz);
+                    const int self = lin3(g, gx, gy, gz0 + j);
+                    const int tl = seed_exact_step(rho, g, W, gx, gy, gz0 + j);
                     if (tl == self) {
                         const unsigned long long s = atomicAdd(root_counter, 1ULL);
                         if ((int64_t)s < roots_cap) roots[s] = self;
                         cde = -2 - (exit_base + (int32_t)s);
                     } else {
-                        cde = F_TILE + tl;
+                        cde = F_T4 + tl;
                     }
                 }
             }
         }
-        s_code[e] = cde;
+        *reinterpret_cast<int32_t *>(reinterpret_cast<char *>(s_code) + eb) = cde;
     };
 
 #pragma unroll 1
@@ -274,30 +278,29 @@ k_seed_pointers(const double *__restrict__ rho, int32_t *code, Grid g, SeedWeigh
     if (tile_keys && threadIdx.x == 0)
         tile_keys[((x0 / FX) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s_key;
     if (!ok0) return;
-    // chase every pointer inside the tile, then store the pair
+    // chase every pointer inside the tile (the pair's two chains in lock step), store the pair
     const bool pair_store = ok1 && ((g.nz & 1) == 0);
+    const char *sc = reinterpret_cast<const char *>(s_code);
+    int v = lin3(g, x0, gy, gz0);
 #pragma unroll 2
-    for (int tx = 0; tx < FX; ++tx) {
-        const int gx = x0 + tx;
-        if (gx >= g.nx) break;
-        const int e = (tx * FY + ty) * FZ + tz0;
-        int32_t c[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            int32_t cc = s_code[e + j];
-            if (cc >= 0 && cc < F_TILE) {
-                do cc = s_code[cc];
-                while (cc >= 0 && cc < F_TILE);
-                s_code[e + j] = cc;  // path compression for the voxels that point here
-            }
-            c[j] = cc >= F_TILE ? cc - F_TILE : cc;
+    for (int tx = 0; tx < FX; ++tx, v += plane) {
+        if (x0 + tx >= g.nx) break;
+        int2 *slot = reinterpret_cast<int2 *>(reinterpret_cast<char *>(s_code) + eb0 + tx * (4 * FY * FZ));
+        int2 c = *slot;
+        if ((unsigned)c.x < (unsigned)F_T4 || (unsigned)c.y < (unsigned)F_T4) {
+            do {
+                if ((unsigned)c.x < (unsigned)F_T4) c.x = *reinterpret_cast<const int32_t *>(sc + c.x);
+                if ((unsigned)c.y < (unsigned)F_T4) c.y = *reinterpret_cast<const int32_t *>(sc + c.y);
+            } while ((unsigned)c.x < (unsigned)F_T4 || (unsigned)c.y < (unsigned)F_T4);
+            *slot = c;  // path compression for the voxels that point here
         }
-        const int v = lin3(g, gx, gy, gz0);
+        c.x = c.x >= F_T4 ? c.x - F_T4 : c.x;
+        c.y = c.y >= F_T4 ? c.y - F_T4 : c.y;
         if (pair_store) {
-            *reinterpret_cast<int2 *>(code + v) = make_int2(c[0], c[1]);
+            *reinterpret_cast<int2 *>(code + v) = c;
         } else {
-            code[v] = c[0];
-            if (ok1) code[v + 1] = c[1];
+            code[v] = c.x;
+            if (ok1) code[v + 1] = c.y;
         }
     }
 }
