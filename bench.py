@@ -188,10 +188,10 @@ def reference_arm(args):
     }))
 
 
-def workload_name(shape):
+def workload_name(shape, mode="('changed',2)"):
     return (f"{shape[0]}x{shape[1]}x{shape[2]} periodic orthorhombic cell, jittered simple-lattice "
             f"Gaussian superposition ({SPACING:.1f}-voxel atom spacing), neargrid + "
-            f"refine('changed',2)")
+            f"refine{mode}")
 
 
 # kernel names behind each family (for the DRAM traffic measured by ncu, profiles/*_traffic.json)
@@ -200,6 +200,10 @@ FAMILY_KERNELS = {'trace': ['k_trace'], 'stencil': ['k_seed_pointers', 'k_ongrid
                   'edge_flag': ['k_label_eq_bits', 'k_edge_from_eq', 'k_edge_deferred'],
                   'edge_dilate': ['k_edge_known'], 'relabel': ['k_relabel_slots'],
                   'first': ['k_first_voxel_slots'], 'edge_confirm': ['k_edge_confirm']}
+
+
+# kernels launched per pass over the grid in the families that chain several kernels
+LAUNCHES_PER_PASS = {'resolve': 4, 'edge_flag': 3}
 
 
 def measured_traffic(family, n_voxels):
@@ -221,6 +225,7 @@ def measured_traffic(family, n_voxels):
                 tot += e['dram_read_bytes'] + e['dram_write_bytes']
                 n += e['launches']
         if n:
+            n /= LAUNCHES_PER_PASS.get(family, 1)
             return {"bytes_per_launch": tot / n, "launches_captured": n,
                     "source": 'profiles/' + os.path.basename(path)}
     return None
@@ -236,8 +241,10 @@ def kernel_accounting(prof, n_voxels, steps, tsteps, tvox, ms_per_step):
         k = {"ms_per_step": ms / steps, "launches_per_step": n / steps}
         if name in ALG_BYTES:
             gb = ALG_BYTES[name] * n_voxels * 1e-9
+            passes = n / LAUNCHES_PER_PASS.get(name, 1)   # full passes over the grid
             k["alg_bytes_per_voxel"] = ALG_BYTES[name]
-            k["achieved_gbs"] = gb / (ms / n * 1e-3)
+            k["passes_per_step"] = passes / steps
+            k["achieved_gbs"] = gb / (ms / passes * 1e-3)
             k["frac"] = k["achieved_gbs"] / peak
         kernels[name] = k
     if 'trace' in kernels and tvox:
@@ -255,8 +262,10 @@ def kernel_accounting(prof, n_voxels, steps, tsteps, tvox, ms_per_step):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": dk['achieved_gbs'], "peak": peak,
                 "unit": "GB/s", "frac": dk['achieved_gbs'] / peak,
                 "traffic": tr and tr['bytes_per_launch'], "traffic_source": tr and tr['source'],
-                "alg_bytes_per_launch": dk['achieved_gbs'] * 1e9 * dk['ms_per_step'] / dk['launches_per_step'] * 1e-3,
-                "peak_source": peak_src, "ms_per_launch": dk['ms_per_step'] / dk['launches_per_step'],
+                "alg_bytes_per_launch": dk['achieved_gbs'] * 1e9 * 1e-3 * dk['ms_per_step']
+                / dk.get('passes_per_step', dk['launches_per_step']),
+                "peak_source": peak_src,
+                "ms_per_launch": dk['ms_per_step'] / dk.get('passes_per_step', dk['launches_per_step']),
                 "share_of_step": dk['ms_per_step'] / ms_per_step}
     return kernels, roofline
 

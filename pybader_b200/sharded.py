@@ -595,7 +595,7 @@ def bench(args, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": B.workload_name(shape), "atoms": len(case['amps']),
+            "config": {"workload": B.workload_name(shape, "('all',2)"), "atoms": len(case['amps']),
                        "maxima": int(sb.maxima.shape[0]), "method": "neargrid",
                        "refine_method": "neargrid", "refine_mode": ["all", 2],
                        "parallelism": f"{world} x-slabs, halo {args.halo} planes, NCCL ring exchange "

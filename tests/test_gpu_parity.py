@@ -295,6 +295,57 @@ def test_neargrid_vs_oracle(th, ut, orc, seeded, mode):
           f"{int(quirk.sum())} vacuum voxels relabelled by the reference only")
 
 
+def test_fp32_seed_equals_exact_seed(th, ut, seeded, monkeypatch):
+    """bader_calc('neargrid') seeds its rounds with the fp32-ranked stencil (csrc/seed.cuh);
+    BDR_SEED_EXACT=1 seeds them with the bit-exact ongrid pointers instead.  Same maxima in
+    the same order, and labels that agree like two runs of the reference do (>= 99.9 %,
+    differences on edge voxels only)."""
+    s = seeded
+    mx, vol = th.bader_calc('neargrid', s['rho'], gpu_fresh(ut, s), s['dist_mat'], s['T_grad'], 1)
+    th.refine('neargrid', ('changed', 2), s['rho'], vol, s['dist_mat'], s['T_grad'], 1)
+    monkeypatch.setenv('BDR_SEED_EXACT', '1')
+    mx2, vol2 = th.bader_calc('neargrid', s['rho'], gpu_fresh(ut, s), s['dist_mat'], s['T_grad'], 1)
+    th.refine('neargrid', ('changed', 2), s['rho'], vol2, s['dist_mat'], s['T_grad'], 1)
+    np.testing.assert_array_equal(mx, mx2)
+    assert np.mean(vol == vol2) >= 0.999
+    assert np.array_equal(vol == -1, vol2 == -1)
+
+
+@pytest.mark.parametrize('shape', [(40, 36, 70), (33, 20, 129), (16, 48, 64)])
+def test_edge_pass_equality_bits_match_minmax_kernel(shape, monkeypatch):
+    """refinement.edge_find through label-equality bits (csrc/edge.cuh) against the min/max
+    streaming kernel it replaced (BDR_EDGE_OLD=1): identical `known` and edge count, on
+    ragged shapes (partial words, nz not a multiple of 4) with and without vacuum"""
+    from pybader_b200.engine import Engine, LABELS_BADER
+    rng = np.random.default_rng(sum(shape))
+    # blocky random labels (edges everywhere), a vacuum slab and scattered vacuum voxels
+    coarse = rng.integers(0, 5, size=tuple((n + 5) // 6 for n in shape))
+    lab = np.kron(coarse, np.ones((6, 6, 6), dtype=np.int64))[:shape[0], :shape[1], :shape[2]]
+    lab = np.ascontiguousarray(lab, dtype=np.int32)
+    rho = rng.random(shape)
+    for vac in (False, True):
+        l = lab.copy()
+        if vac:
+            l[:, :, shape[2] // 2: shape[2] // 2 + 9] = -1
+            l[rng.random(shape) < 0.02] = -1
+            l[0, 0, 0] = -1
+            l[-1, -1, -1] = -1
+        out = []
+        for old in (False, True):
+            if old:
+                monkeypatch.setenv('BDR_EDGE_OLD', '1')
+            else:
+                monkeypatch.delenv('BDR_EDGE_OLD', raising=False)
+            e = Engine(shape)
+            e.upload_density(0, rho)
+            e.upload_labels(LABELS_BADER, l)
+            n = e.edge_find(LABELS_BADER)
+            out.append((n, e.download_known()))
+            e.close()
+        assert out[0][0] == out[1][0]
+        np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
 # ------------------------------------------------ properties at size -------
 def test_properties_256(th, ut):
     """size-independent properties on a 256^3 rocksalt cell (BASELINE config 2
