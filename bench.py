@@ -130,7 +130,7 @@ def cpu_step(orc, rho, dist, T):
     return vol
 
 
-def cpu_baseline_leg(n=176):
+def cpu_baseline_leg(n=256):
     from oracle import pyoracle as orc
     rho, dist, T = cpu_sample_inputs(n)
     cpu_step(orc, rho[:32, :32, :32].copy(), dist, T)          # load / warm the .so
@@ -278,8 +278,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=0, help='override: cubic N^3 single-GPU grid')
-    ap.add_argument('--cpu-sample', type=int, default=176)
-    ap.add_argument('--ref-sample', type=int, default=112)
+    ap.add_argument('--cpu-sample', type=int, default=256)
+    ap.add_argument('--ref-sample', type=int, default=160)
     ap.add_argument('--halo', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')

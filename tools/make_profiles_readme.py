@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""profiles/README.md from the committed bench lines, traffic capture and ncu summaries.
+
+    python tools/make_profiles_readme.py r1v13 > profiles/README.md
+"""
+import glob
+import json
+import os
+import sys
+
+tag = sys.argv[1]
+P = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles')
+
+
+def load(name):
+    with open(os.path.join(P, name)) as f:
+        return json.loads(f.read().strip().splitlines()[-1])
+
+
+b = load(f'{tag}_bench_1024.json')
+ref = load(f'{tag}_bench_ref.json')
+with open(os.path.join(P, f'{tag}_traffic.json')) as f:
+    tr = json.load(f)
+N = 1024 ** 3
+fam_k = {'stencil': ['k_seed_pointers'], 'resolve': ['k_tile_hist', 'k_tile_scan', 'k_tile_scatter', 'k_resolve_tiles'],
+         'relabel': ['k_relabel_slots'], 'edge_flag': ['k_label_eq_bits', 'k_edge_from_eq', 'k_edge_deferred'],
+         'edge_dilate': ['k_edge_known'], 'trace': ['k_trace'], 'first': ['k_first_voxel_slots'],
+         'edge_confirm': ['k_edge_confirm', 'k_edge_fix_clear', 'k_edge_fix_known', 'k_edge_fix_tomb'],
+         'edge_check': ['k_filter_cached', 'k_inc_collect', 'k_inc_classify', 'k_inc_dilate', 'k_inc_mark',
+                        'k_compact_known', 'k_bits_from_list', 'k_ec_init', 'k_ec_round', 'k_ec_collect_centres',
+                        'k_ec_classify', 'k_ec_dilate', 'k_ec_finish']}
+out = []
+w = out.append
+w(f"# profiles/ — measured evidence ({tag})\n")
+w("Everything here was produced on one NVIDIA B200 (sm_100a, 148 SMs) through `gpurun` by "
+  "`tools/gpu_round.sh` (single GPU) and the torchrun lines in `tools/gpu_scale.sh` (2/4/8 GPUs).  "
+  "Numbers printed under ncu are never bench values: bench values come from `bench.py` (CUDA events on "
+  "the library's stream), ncu supplies launch lists, DRAM traffic and the `--set full` details.\n")
+w("## Headline (N = 1, 1024³, neargrid + refine('changed', 2))\n")
+w("| quantity | value |\n|---|---|")
+w(f"| step, density resident (`value`) | {b['ms_per_step']:.2f} ms → {b['value'] / 1e9:.2f} Gvoxel/s |")
+e = b['e2e']
+w(f"| end to end through `bdr_run`, host buffers (`e2e`) | {e['ms_per_step']:.1f} ms → {e['value'] / 1e9:.2f} Gvoxel/s "
+  f"({e['h2d_bytes_per_step'] / 1e9:.2f} GB H2D + {e['d2h_bytes_per_step'] / 1e9:.2f} GB D2H per step; PCIe-bound) |")
+c = b['cpu_baseline']
+if c:
+    w(f"| CPU oracle port, 1 core (`cpu_baseline`) | {c['value'] / 1e6:.2f} Mvoxel/s ({c['sample'].split(',')[0]}) |")
+w(f"| reference arm (`--impl reference`, {ref['cpu_baseline']['cores']} host threads) | {ref['value'] / 1e6:.1f} Mvoxel/s |")
+w(f"| kernels launched per step (`gpu_launches` / steps) | {b['gpu_launches'] / b['steps']:.0f} |")
+w(f"| SM clock during the timed region | {b['clocks']['sm_mhz']} MHz of {b['clocks']['sm_max_mhz']} (reasons: {b['clocks']['reasons'] or 'none'}) |")
+r = b['roofline']
+w(f"| `roofline` (dominant family: {r['kernel']}) | achieved {r['achieved']:.0f} GB/s algorithmic of {r['peak']:.0f} GB/s "
+  f"({r['peak_source']}) = {r['frac']:.3f}; DRAM traffic per launch {((r.get('traffic') or 0) / 1e9):.2f} GB vs "
+  f"{r.get('alg_bytes_per_launch', 0) / 1e9:.2f} GB algorithmic (gathers are served by L1/L2) |\n")
+w("## Per kernel family, one step (CUDA events in bench.py; DRAM bytes from the ncu pass over every launch)\n")
+w("| family | kernels | ms / step | launches | alg. B/voxel | achieved GB/s | frac of HBM peak | DRAM GB read+written (ncu) | alg. GB |")
+w("|---|---|---|---|---|---|---|---|---|")
+for name, k in sorted(b['kernels'].items(), key=lambda kv: -kv[1]['ms_per_step']):
+    ks = fam_k.get(name, [])
+    dr = sum(tr['kernels'][x]['dram_read_bytes'] + tr['kernels'][x]['dram_write_bytes'] for x in ks if x in tr['kernels'])
+    alg = k.get('alg_bytes_per_voxel')
+    algb = (alg * N * k.get('passes_per_step', 1) / 1e9) if alg else (k.get('alg_bytes_per_launch', 0) * k['launches_per_step'] / 1e9)
+    w(f"| {name} | {', '.join('`%s`' % x for x in ks if x in tr['kernels']) or '—'} | {k['ms_per_step']:.2f} | "
+      f"{k['launches_per_step']:.0f} | {alg if alg else '—'} | "
+      f"{k.get('achieved_gbs', 0):.0f} | {k.get('frac', 0):.3f} | {dr / 1e9:.2f} | {algb:.2f} |")
+w(f"\nSum of the families: {sum(k['ms_per_step'] for k in b['kernels'].values()):.2f} ms of the {b['ms_per_step']:.2f} ms step; "
+  "the rest is host round trips between data-dependent launches (counter read-backs).\n")
+w("## Files\n")
+for f in sorted(os.listdir(P)):
+    if f == 'README.md':
+        continue
+    what = {'bench_1024.json': "bench.py line, N=1", 'bench_ref.json': "bench.py --impl reference line",
+            'launches_1024.csv': "ncu launch list (gpu__time_duration.sum) of `bench.py --steps 1 --warmup 3`",
+            'traffic.json': "DRAM bytes and duration of every launch of one step (tools/ncu_traffic.py)",
+            'ncu_set_full_1024.txt': "key metrics of the `--set full` captures of the top kernels (tools/ncu_summary.py)",
+            'pytest_gpu.log': "`pytest -m gpu` on the box", 'smoke.log': "`__graft_entry__.smoke()`"}
+    desc = next((v for k, v in what.items() if f.endswith(k)), '')
+    if '_bench_n' in f:
+        desc = "bench.py line under torchrun, N = " + f.split('_bench_n')[1].split('.')[0]
+    w(f"* `{f}` — {desc or 'earlier capture of this round, kept for the history of the kernels'}")
+print('\n'.join(out))
