@@ -575,46 +575,78 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
     if (getenv("BDR_TRACE_CHUNK")) chunk = std::min(chunk, atoi(getenv("BDR_TRACE_CHUNK")));
     const int64_t n_warps = (n + chunk - 1) / chunk;
     const PeerView *pv = static_cast<const PeerView *>(c->peer_view);
-    if (pv)
-        LAUNCH(c, BDR_K_TRACE, (k_trace_peer<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
-               *pv, c->labels[which], c->known, c->g, window_of(c), W, T, c->list, n, chunk,
-               (long long *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
-               c->list2_cap, c->list3, c->list3_cap, step_cap,
-               c->use_term ? c->term : (int32_t *)nullptr);
-    else
+    int32_t *chg = want_changed_list ? c->list2 : (int32_t *)nullptr;
+    int32_t *term = c->use_term ? c->term : (int32_t *)nullptr;
+    constexpr int SLOW_CAP = 4096;
+    const int64_t batch = 16384;
+    // stage 1: the local kernel.  On a slab window it may only read classification and
+    // labels on the planes this rank owns; walks that step off them (and over-long ones)
+    // come back in c->list3
+    Window win = window_of(c);
+    const bool local_first = pv && c->halo >= 3 && !getenv("BDR_TRACE_PEER_ONLY");
+    if (local_first) {
+        win.xlo = c->halo;
+        win.xhi = c->g.nx - c->halo - 1;
+    }
+    if (!pv || local_first) {
         LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
-               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c), W, T,
-               c->list, n, chunk, (int32_t *)nullptr, c->d_cnt, want_changed_list ? c->list2 : (int32_t *)nullptr,
-               c->list2_cap, c->list3, c->list3_cap, step_cap, c->use_term ? c->term : (int32_t *)nullptr);
-    TRY(read_counters(c));
-    if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
-    const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
-    if (ov > 0) {
-        // long paths: redo those voxels with a path buffer in global memory,
-        // in batches so the scratch stays bounded (SLOW_CAP * 4 B per voxel)
-        constexpr int SLOW_CAP = 4096;
-        const int64_t batch = 16384;
-        TRY(ensure_stage(c, (size_t)(std::min(ov, batch) + 128) * SLOW_CAP * sizeof(long long)));
-        CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
-        for (int64_t o = 0; o < ov; o += batch) {
-            const int64_t m = std::min(batch, ov - o);
-            if (pv)
-                LAUNCH(c, BDR_K_TRACE, (k_trace_peer<SLOW_CAP, true>), blocks_for(m, 128), 128, 0, *pv,
-                       c->labels[which], c->known, c->g, window_of(c), W, T, c->list3 + o, m, 32,
-                       (long long *)c->stage, c->d_cnt,
-                       want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
-                       (int32_t *)nullptr, (int64_t)0, step_cap,
-                       c->use_term ? c->term : (int32_t *)nullptr);
-            else
+               rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, win, W, T, c->list, n,
+               chunk, (int32_t *)nullptr, c->d_cnt, chg, c->list2_cap, c->list3, c->list3_cap, step_cap,
+               term, local_first ? 1 : 0);
+        TRY(read_counters(c));
+        if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
+    }
+    if (!pv) {
+        const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
+        if (ov > 0) {
+            // long paths: redo those voxels with a path buffer in global memory,
+            // in batches so the scratch stays bounded (SLOW_CAP * 4 B per voxel)
+            TRY(ensure_stage(c, (size_t)(std::min(ov, batch) + 128) * SLOW_CAP * sizeof(long long)));
+            CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
+            for (int64_t o = 0; o < ov; o += batch) {
+                const int64_t m = std::min(batch, ov - o);
                 LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
                        rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
-                       W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt,
-                       want_changed_list ? c->list2 : (int32_t *)nullptr, c->list2_cap,
-                       (int32_t *)nullptr, (int64_t)0, step_cap,
-                       c->use_term ? c->term : (int32_t *)nullptr);
+                       W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt, chg, c->list2_cap,
+                       (int32_t *)nullptr, (int64_t)0, step_cap, term, 0);
             }
-        TRY(read_counters(c));
-        if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
+            TRY(read_counters(c));
+            if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
+        }
+    } else {
+        // stage 2 (slab windows): the peer kernel continues on the neighbours' memory
+        // (K4p) -- over the walks stage 1 handed back, or over the whole list
+        const int32_t *in = c->list;
+        int64_t m_in = n;
+        if (local_first) {
+            in = c->list3;
+            m_in = (int64_t)c->h_cnt[CNT_OVERFLOW];
+        }
+        if (m_in > 0) {
+            TRY(ensure(&c->list4, &c->list4_cap, m_in));
+            CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
+            const int pchunk = local_first ? 32 : chunk;
+            LAUNCH(c, BDR_K_TRACE, (k_trace_peer<PATH_FAST, false>),
+                   blocks_for((m_in + pchunk - 1) / pchunk * 32, 128), 128, 0, *pv, c->labels[which],
+                   c->known, c->g, window_of(c), W, T, in, m_in, pchunk, (long long *)nullptr, c->d_cnt,
+                   chg, c->list2_cap, c->list4, c->list4_cap, step_cap, term);
+            TRY(read_counters(c));
+            if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
+            const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
+            if (ov > 0) {
+                TRY(ensure_stage(c, (size_t)(std::min(ov, batch) + 128) * SLOW_CAP * sizeof(long long)));
+                CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
+                for (int64_t o = 0; o < ov; o += batch) {
+                    const int64_t m = std::min(batch, ov - o);
+                    LAUNCH(c, BDR_K_TRACE, (k_trace_peer<SLOW_CAP, true>), blocks_for(m, 128), 128, 0, *pv,
+                           c->labels[which], c->known, c->g, window_of(c), W, T, c->list4 + o, m, 32,
+                           (long long *)c->stage, c->d_cnt, chg, c->list2_cap, (int32_t *)nullptr,
+                           (int64_t)0, step_cap, term);
+                }
+                TRY(read_counters(c));
+                if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
+            }
+        }
     }
     *changed = (int64_t)c->h_cnt[CNT_CHANGED];
     c->escaped = (int64_t)c->h_cnt[CNT_ESCAPED];
@@ -1108,7 +1140,7 @@ int bdr_destroy(bdr_ctx *c) {
                     (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
                     (void *)c->d_sums, c->stage, (void *)c->ebits, (void *)c->term,
                     (void *)c->tile_keys, (void *)c->tile_order, (void *)c->tile_hist,
-                    (void *)c->d_seedw, (void *)c->defer})
+                    (void *)c->d_seedw, (void *)c->defer, (void *)c->list4})
         if (p) cudaFree(p);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->pinned) cudaFreeHost(c->pinned);

@@ -120,6 +120,8 @@ struct bdr_ctx {
     int64_t list2_cap = 0;
     int32_t *list3 = nullptr;  // centres (edge_check)
     int64_t list3_cap = 0;
+    int32_t *list4 = nullptr;  // slab windows: over-long walks of the peer trace kernel
+    int64_t list4_cap = 0;
 
     int32_t *roots = nullptr;  // voxel index of each maximum, by slot
     int32_t *minidx = nullptr; // first voxel (C order) of each slot's volume

@@ -146,6 +146,21 @@ class ShardedBader:
         t[:H].copy_(lo)
         t[self.W - H:].copy_(hi)
 
+    def _phase(self, name):
+        """BDR_PHASES=1: wall-clock per phase of the protocol (device drained at every
+        boundary, so the step runs slower while this is on)"""
+        if not os.environ.get('BDR_PHASES'):
+            return
+        import time
+        torch.cuda.synchronize()
+        if hasattr(self.backend, '_sync'):
+            self.backend.check(self.backend.lib.bdr_synchronize(self.backend.h))
+        now = time.perf_counter()
+        acc = self.__dict__.setdefault('phase_ms', {})
+        if getattr(self, '_phase_name', None) is not None:
+            acc[self._phase_name] = acc.get(self._phase_name, 0.0) + (now - self._phase_t0) * 1e3
+        self._phase_name, self._phase_t0 = name, now
+
     # ---- ongrid: seed, exits, numbering -----------------------------------
     def _dbg(self, msg):
         if os.environ.get('BDR_DEBUG'):
@@ -154,7 +169,9 @@ class ShardedBader:
     def ongrid(self, dist_mat, method='ongrid'):
         be, H, P = self.backend, self.halo, self.plane
         self._dbg("seed")
+        self._phase('seed')
         n_real, exit_base = be.seed(dist_mat, method)
+        self._phase('exits')
         self._dbg(f"seeded: {n_real} local maxima")
         codes = be.labels()                      # int32 [W, ny, nz]: -1 vacuum, -2-s slots
         dev = codes.device
@@ -196,6 +213,7 @@ class ShardedBader:
 
         # first owned voxel of every slot -> per root id
         self._dbg("numbering")
+        self._phase('numbering')
         first_w = be.first_voxel(n_slots).to(torch.int64)          # window-linear or NO_VOXEL
         used = first_w != NO_VOXEL
         if bool((G[used] == UNRESOLVED).any()):
@@ -224,7 +242,9 @@ class ShardedBader:
             vals = torch.where(hit, number_of[pos], torch.full_like(pos, -1)).to(torch.int32)
             rank_lut[ok] = vals
         self._dbg("apply rank")
+        self._phase('apply_rank')
         be.apply_rank(rank_lut)
+        self._phase(None)
         self._dbg("ongrid done")
         mg = uniq[order].cpu().numpy()
         self.maxima = np.stack([mg // P, (mg // self.nz) % self.ny, mg % self.nz], axis=1)
@@ -239,12 +259,16 @@ class ShardedBader:
         it = 0
         dbg = os.environ.get('BDR_DEBUG') and self.comm.rank == 0
         while iters < 0 or it < iters:
+            self._phase('refine:halo')
             self.exchange_halo(be.labels())
+            self._phase('refine:edge_pass')
             edges = be.edge_pass()
             # every rank's classification must be complete before any rank's
             # trajectories may read it (remote reads in the trace kernel)
             edges = self.comm.allreduce_sum(edges, dev)
+            self._phase('refine:trace')
             changed, escaped = be.trace_pass(dist_mat, T_grad)
+            self._phase('refine:reduce')
             if self.comm.allreduce_sum(escaped, dev):
                 raise RuntimeError("a trajectory left the slab halo: raise `halo`")
             changed = self.comm.allreduce_sum(changed, dev)
@@ -254,7 +278,9 @@ class ShardedBader:
             it += 1
             if changed == 0 or edges == 0:
                 break
+        self._phase('refine:halo')
         self.exchange_halo(be.labels())
+        self._phase(None)
         return history
 
     def neargrid(self, dist_mat, T_grad, max_passes=64):
@@ -271,23 +297,31 @@ class ShardedBader:
             return self.maxima
         dev, H, P = be.labels().device, self.halo, self.plane
         lab = be.labels()
+        self._phase('rounds:halo')
         self.exchange_halo(lab)
+        self._phase('rounds:first_pass')
         edges = self.comm.allreduce_sum(be.first_pass(), dev)      # also the barrier before remote reads
+        self._phase('rounds:trace')
         changed = self.comm.allreduce_sum(be.trace(dist_mat, T_grad, True), dev) if edges else 0
         hist = [(edges, changed)]
         self._dbg(f"first pass: edges {edges} changed {changed}")
         while changed > 0 and len(hist) < max_passes:
             # the planes next to the owned slab, before and after the exchange
+            self._phase('rounds:halo')
             old_lo, old_hi = lab[H - 1].clone(), lab[self.W - H].clone()
             self.exchange_halo(lab)
+            self._phase('rounds:requeue')
             lo = torch.nonzero((lab[H - 1] != old_lo).reshape(-1)).reshape(-1) + (H - 1) * P
             hi = torch.nonzero((lab[self.W - H] != old_hi).reshape(-1)).reshape(-1) + (self.W - H) * P
             extra = torch.cat([lo, hi]).to(torch.int32)
             queued = self.comm.allreduce_sum(be.requeue(extra), dev)
+            self._phase('rounds:trace')
             changed = self.comm.allreduce_sum(be.trace(dist_mat, T_grad, True), dev)
             hist.append((queued, changed))
             self._dbg(f"round {len(hist) - 1}: queued {queued} changed {changed}")
+        self._phase('rounds:halo')
         self.exchange_halo(lab)
+        self._phase(None)
         self.settled = changed == 0
         self.neargrid_history = hist
         return self.maxima
@@ -587,6 +621,10 @@ def bench(args, rank, world, local):
                "api": "per rank: bdr_upload_density(window, pinned host) + sharded step + "
                       "bdr_download_labels(narrowed); max over ranks"}
         del host_rho, host_lab
+    if rank == 0 and getattr(sb, 'phase_ms', None):
+        nst = args.warmup + args.steps * (1 if args.no_e2e else 2) + (0 if args.no_e2e else 1)
+        print("[sharded] phases, ms per step (BDR_PHASES): " +
+              ", ".join(f"{k} {v / nst:.2f}" for k, v in sb.phase_ms.items()), file=sys.stderr)
     if rank == 0:
         kernels, roofline = B.kernel_accounting(prof, be.N, args.steps, ts.value, tv.value, ms_per_step)
         roofline["note"] = "rank 0's kernels on its slab window; the step also holds NCCL exchanges"
