@@ -346,6 +346,55 @@ def test_edge_pass_equality_bits_match_minmax_kernel(shape, monkeypatch):
         np.testing.assert_array_equal(out[0][1], out[1][1])
 
 
+# ---------------------------------------- BASELINE configs 1 and 2, full size ----
+def _case_dict(name, c, tol=None):
+    from pybader_b200 import geometry as geo, synth
+    # orthorhombic cells factorise: 256^3 from 1-D tables in a fraction of a second
+    tx, ty, tz = synth.separable_tables(c)
+    rho = np.ascontiguousarray(np.einsum('ai,aj,ak->ijk', tx, ty, tz, optimize=True))
+    atoms = c['frac_atoms'] @ c['lattice']
+    return dict(name=name, rho=rho, atoms=atoms, lattice=c['lattice'], vacuum_tol=tol,
+                dist_mat=geo.distance_matrix(c['lattice'], rho.shape),
+                T_grad=geo.T_grad(c['lattice'], rho.shape),
+                voxel_volume=geo.voxel_volume(c['lattice'], rho.shape))
+
+
+def test_config1_full_size_vs_oracle(th, ut, orc):
+    """BASELINE config 1: 3-atom cubic cell 96^3, neargrid + refine ('changed', 2), against the
+    (reference-pinned) oracle: labels >= 99.9 % identical with differences on Bader surfaces
+    only, same maxima, charges and volumes within 1e-6"""
+    from pybader_b200 import synth
+    s = _case_dict('c1_96', synth.case_c1(96))
+    mx, vol = th.bader_calc('neargrid', s['rho'], gpu_fresh(ut, s), s['dist_mat'], s['T_grad'], 1)
+    th.refine('neargrid', ('changed', 2), s['rho'], vol, s['dist_mat'], s['T_grad'], 1)
+    rmx, rvol = orc.bader_calc('neargrid', s['rho'], oracle_fresh(orc, s), s['dist_mat'], s['T_grad'])
+    orc.refine('neargrid', ('changed', 2), s['rho'], rvol, s['dist_mat'], s['T_grad'])
+    key = lambda m: sorted(map(tuple, m.tolist()))
+    assert key(mx) == key(rmx)
+    ndiff = check_neargrid(vol, mx, rvol, rmx, s['rho'], orc, s['name'])
+    order = {tuple(m): i for i, m in enumerate(rmx.tolist())}
+    perm = np.array([order[tuple(m)] for m in mx.tolist()])
+    n = mx.shape[0]
+    q, v, rq, rv = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    ut.charge_sum(q, v, s['voxel_volume'], s['rho'], vol)
+    orc.charge_sum(rq, rv, s['voxel_volume'], s['rho'], rvol)
+    np.testing.assert_allclose(q, rq[perm], rtol=REL_TOL)
+    np.testing.assert_allclose(v, rv[perm], rtol=REL_TOL)
+    print(f"config 1 (96^3): {ndiff} of {vol.size} voxels differ from the reference path")
+
+
+def test_config2_full_size_ongrid_bit_exact(th, ut, orc):
+    """BASELINE config 2: rocksalt-like 64-atom cell 256^3, method=ongrid: maxima list, labels
+    and label dtype bit-identical to the oracle (tie-breaking included)"""
+    from pybader_b200 import synth
+    s = _case_dict('rocksalt256', synth.case_rocksalt(256, cells=4, offset=0.13))
+    mx, vol = th.bader_calc('ongrid', s['rho'], gpu_fresh(ut, s), s['dist_mat'], s['T_grad'], 1)
+    rmx, rvol = orc.bader_calc('ongrid', s['rho'], oracle_fresh(orc, s), s['dist_mat'], s['T_grad'])
+    np.testing.assert_array_equal(mx, rmx)
+    assert vol.dtype == rvol.dtype
+    np.testing.assert_array_equal(vol, rvol)
+
+
 # ------------------------------------------------ properties at size -------
 def test_properties_256(th, ut):
     """size-independent properties on a 256^3 rocksalt cell (BASELINE config 2
