@@ -219,6 +219,27 @@ int bdr_slab_ipc_export(bdr_ctx *ctx, void *handles);
 int bdr_slab_ipc_attach(bdr_ctx *ctx, int world, int rank, const void *all_handles,
                         const int64_t *bounds, int64_t nx_global);
 
+/* ---- text -> grid: the numeric block of a CHGCAR / cube file ---
+ * Replaces the token-by-token numpy conversion of io/vasp.py:90-137 (charge and
+ * spin blocks; values / cell volume; file order x fastest -> [x][y][z]) and
+ * io/cube.py:99-113 (values * bohr^-3, file order already [x][y][z]).
+ * `text` holds whitespace-separated decimal tokens; the first n_values = nx*ny*nz
+ * of them are converted (correctly rounded, like Python's float) on the GPU and
+ * written to `out` in C order [nx][ny][nz].  x_fastest: token t is voxel
+ * (t % nx, (t / nx) % ny, t / (nx * ny)).  op: 0 none, 1 out = v / operand,
+ * 2 out = v * operand.  Tokens the device cannot convert exactly (more than 19
+ * digits, '****', nan, exponents beyond its tables, subnormal results) leave NaN
+ * in `out` and are reported as (token index, byte offset, byte length) triples:
+ * the caller converts those with its own strtod / float() and applies `op`
+ * (reference behaviour, including its ValueError on junk).                    */
+int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_values, int64_t nx,
+                   int64_t ny, int64_t nz, int x_fastest, int op, double operand, double *out,
+                   int64_t *tokens_found, int64_t *bytes_consumed, int64_t *n_fallback,
+                   int64_t *fallback, int64_t fallback_cap);
+/* the same conversion for one token on the CPU (tests; no device needed):
+ * 0 converted, 2 not handled exactly (ask strtod)                             */
+int bdr_parse_token_host(const char *token, int64_t len, double *out);
+
 /* ---- options ------------------------------------------------------------- */
 /* BDR_OPT_VERIFY_FIXED_POINT (default 0): bader_calc('neargrid') drives the
  * labels to quiescence with one full edge pass plus incremental rounds; with

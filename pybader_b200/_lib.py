@@ -65,6 +65,9 @@ SIGNATURES = {
     "bdr_selftest_div": ([_p, _i64, ctypes.c_uint64, ctypes.POINTER(_i64)], _int),
     "bdr_set_option": ([_p, _int, _i64], _int),
     "bdr_device_ptr": ([_p, _int, _pp], _int),
+    "bdr_parse_text": ([_int, _p, _i64, _i64, _i64, _i64, _i64, _int, _int, _f64, _p,
+                        ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64), _p, _i64], _int),
+    "bdr_parse_token_host": ([ctypes.c_char_p, _i64, ctypes.POINTER(_f64)], _int),
 }
 
 _lib = None

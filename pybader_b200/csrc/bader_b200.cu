@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "seed.cuh"
 #include "edge.cuh"
+#include "parse.cuh"
 
 #include <chrono>
 #include <cstdlib>
@@ -1476,6 +1477,112 @@ int bdr_run(bdr_ctx *c, const double *host_density, double vac_tol, double voxel
     if (dbg)
         fprintf(stderr, "[bdr] run: upload+bader_calc %.1f ms (upload+stencil %.1f), refine %.1f ms, sums+download %.1f ms\n",
                 t1 - t0, c->dbg_upload_ms, t2 - t1, now() - t2);
+    return 0;
+}
+
+// ---- text -> grid --------------------------------------
+int bdr_parse_token_host(const char *token, int64_t len, double *out) {
+    if (!token || !out || len <= 0) return fail_msg("bdr_parse_token_host: bad argument");
+    int l = 0;
+    const int st = parse_token(token, len, out, &l);
+    return (st == 0 && l == len) ? 0 : 2;   // 2: not handled exactly here, ask the host's strtod
+}
+
+int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_values, int64_t nx,
+                   int64_t ny, int64_t nz, int x_fastest, int op, double operand, double *out,
+                   int64_t *tokens_found, int64_t *bytes_consumed, int64_t *n_fallback,
+                   int64_t *fallback, int64_t fallback_cap) {
+    if (!text || !out || nbytes < 0 || n_values <= 0 || nx * ny * nz != n_values)
+        return fail_msg("bdr_parse_text: bad argument");
+    if (n_values >= (1LL << 31)) return fail_msg("bdr_parse_text: more than 2^31 values");
+    CU(cudaSetDevice(device));
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const int64_t CHUNK = 256LL << 20;
+    const int64_t cbytes = std::min<int64_t>(std::max<int64_t>(nbytes, 1), CHUNK);
+    const int64_t max_blocks = (cbytes + TOK_BLOCK - 1) / TOK_BLOCK;
+    char *d_text = nullptr;
+    double *d_vals = nullptr, *d_out = nullptr;
+    unsigned *d_counts = nullptr, *d_tot1 = nullptr, *d_tot2 = nullptr;
+    ParseOut *d_po = nullptr;
+    int64_t *d_fb = nullptr;
+    const int64_t fb_cap = std::max<int64_t>(fallback_cap, 0);
+    auto cleanup = [&]() {
+        for (void *p : {(void *)d_text, (void *)d_vals, (void *)d_out, (void *)d_counts, (void *)d_tot1,
+                        (void *)d_tot2, (void *)d_po, (void *)d_fb})
+            if (p) cudaFree(p);
+        cudaStreamDestroy(st);
+    };
+#define PCU(x)                                                    \
+    do {                                                          \
+        cudaError_t e_ = (x);                                     \
+        if (e_ != cudaSuccess) {                                  \
+            cleanup();                                            \
+            return bdr::fail(#x, __FILE__, __LINE__, e_);         \
+        }                                                         \
+    } while (0)
+    PCU(cudaMalloc((void **)&d_text, (size_t)cbytes + 64));
+    PCU(cudaMalloc((void **)&d_vals, (size_t)n_values * sizeof(double)));
+    PCU(cudaMalloc((void **)&d_out, (size_t)n_values * sizeof(double)));
+    PCU(cudaMalloc((void **)&d_counts, (size_t)max_blocks * sizeof(unsigned)));
+    PCU(cudaMalloc((void **)&d_tot1, 1024 * sizeof(unsigned)));
+    PCU(cudaMalloc((void **)&d_tot2, 1024 * sizeof(unsigned)));
+    PCU(cudaMalloc((void **)&d_po, sizeof(ParseOut)));
+    PCU(cudaMalloc((void **)&d_fb, (size_t)std::max<int64_t>(fb_cap, 1) * 3 * sizeof(int64_t)));
+    PCU(cudaMemsetAsync(d_po, 0, sizeof(ParseOut), st));
+    // values no token reaches read as NaN
+    PCU(cudaMemsetAsync(d_vals, 0xff, (size_t)n_values * sizeof(double), st));
+    int64_t pos = 0, tokens = 0;
+    while (pos < nbytes && tokens < n_values) {
+        // a chunk ends on whitespace, so no token straddles two chunks
+        int64_t end = std::min(nbytes, pos + CHUNK);
+        if (end < nbytes) {
+            int64_t e = end;
+            while (e > pos && !is_space((unsigned char)text[e - 1])) --e;
+            if (e == pos) {
+                cleanup();
+                return fail_msg("bdr_parse_text: a token longer than the chunk size");
+            }
+            end = e;
+        }
+        const int64_t n = end - pos;
+        const int64_t nb = (n + TOK_BLOCK - 1) / TOK_BLOCK, n1 = (nb + 1023) / 1024;
+        PCU(cudaMemcpyAsync(d_text, text + pos, (size_t)n, cudaMemcpyHostToDevice, st));
+        k_tok_count<<<(unsigned)nb, 256, 0, st>>>(d_text, n, d_counts);
+        k_scan_local<<<(unsigned)n1, 1024, 0, st>>>(d_counts, nb, d_tot1);
+        k_scan_local<<<1, 1024, 0, st>>>(d_tot1, n1, d_tot2);
+        k_scan_add<<<(unsigned)n1, 1024, 0, st>>>(d_counts, nb, d_tot1);
+        k_tok_parse<<<(unsigned)nb, 256, 0, st>>>(d_text, n, d_counts, tokens, pos, d_vals, n_values, d_po,
+                                                  d_fb, fb_cap);
+        unsigned chunk_tokens = 0;
+        PCU(cudaMemcpyAsync(&chunk_tokens, d_tot2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        PCU(cudaStreamSynchronize(st));
+        PCU(cudaGetLastError());
+        tokens += chunk_tokens;
+        pos = end;
+    }
+    ParseOut po;
+    PCU(cudaMemcpyAsync(&po, d_po, sizeof(ParseOut), cudaMemcpyDeviceToHost, st));
+    PCU(cudaStreamSynchronize(st));
+    const int64_t found = std::min(tokens, n_values);
+    if (tokens_found) *tokens_found = found;
+    if (bytes_consumed) *bytes_consumed = tokens >= n_values ? (int64_t)po.end_of_last : nbytes;
+    if (n_fallback) *n_fallback = (int64_t)po.n_fallback;
+    if (fallback && fb_cap > 0 && po.n_fallback > 0)
+        PCU(cudaMemcpyAsync(fallback, d_fb,
+                            (size_t)std::min<int64_t>((int64_t)po.n_fallback, fb_cap) * 3 * sizeof(int64_t),
+                            cudaMemcpyDeviceToHost, st));
+    if (x_fastest) {
+        const dim3 grid((unsigned)(((nx + 31) / 32) * ((nz + 31) / 32)), (unsigned)ny);
+        k_grid_finish<<<grid, 256, 0, st>>>(d_vals, d_out, (int)nx, (int)ny, (int)nz, 1, op, operand);
+    } else {
+        k_grid_finish<<<148 * 8, 256, 0, st>>>(d_vals, d_out, (int)nx, (int)ny, (int)nz, 0, op, operand);
+    }
+    PCU(cudaGetLastError());
+    PCU(cudaMemcpyAsync(out, d_out, (size_t)n_values * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PCU(cudaStreamSynchronize(st));
+#undef PCU
+    cleanup();
     return 0;
 }
 

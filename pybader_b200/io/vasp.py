@@ -1,0 +1,132 @@
+"""CHGCAR / CHG reader: the reference's `pybader.io.vasp.read` (io/vasp.py:15-164)
+with the density blocks converted on the GPU.  Same arguments, same return
+tuple, same arithmetic (tokens -> float64, / cell volume, [x][y][z] C order)."""
+import os
+from time import time
+
+import numpy as np
+
+from ._text import OP_DIVIDE, parse_block
+
+
+def _read_block(f, n_values, est_bytes):
+    """bytes of a block of n_values tokens starting at the file position: the
+    reference's fixed-line-length estimate plus slack, grown if tokens are missing"""
+    start = f.tell()
+    f.seek(0, 2)
+    end = f.tell()
+    f.seek(start)
+    want = min(end - start, est_bytes + 4096)
+    return start, end, np.fromfile(f, dtype=np.uint8, count=want)
+
+
+def read(fn, charge_flag=True, spin_flag=False, buffer_size=64, device=0):
+    """Read the charge and/or spin density from a VASP CHGCAR (io/vasp.py:15-164).
+
+    return: density dict, lattice (rows), atoms (Cartesian), file_info"""
+    t0 = time()
+    density = dict()
+    prefix, filename = os.path.split(fn)
+    prefix = os.path.join(prefix, '')
+    with open(fn, 'rb') as f:
+        print(f"  Reading {fn} as CHGCAR format.")
+        _ = f.readline()                                   # comment line of the POSCAR
+        scale = np.array(f.readline().split(), dtype=np.float64)
+        lattice = np.zeros((3, 3), dtype=np.float64)
+        for i in range(3):
+            lattice[i] = f.readline().split()
+        atom_types = [t.decode() for t in f.readline().split()]
+        try:
+            atom_nums = np.array(atom_types, dtype=np.int64)   # no symbols line
+            atom_types = None
+        except ValueError:
+            atom_nums = np.array(f.readline().split(), dtype=np.int64)
+        atom_sum = int(atom_nums.sum())
+        coord_system = f.readline().lstrip().lower()
+        atoms = np.zeros((atom_sum, 3), dtype=np.float64)
+        for i in range(atom_sum):
+            atoms[i] = f.readline().split()
+        if coord_system[:1] == b'd':
+            atoms %= 1
+        else:
+            atoms = np.dot(atoms, np.linalg.inv(lattice))
+            atoms %= 1
+        _ = f.readline()
+        grid_line = f.readline()
+        grid = np.array(grid_line.split(), dtype=np.int64)
+        grid_pts = int(np.prod(grid))
+        print(f"  {' x '.join(grid.astype(str))} grid size.")
+        charge_pos = f.tell()
+        first = f.readline()
+        per_line = max(len(first.split()), 1)
+        line_len = len(first)
+        est = (grid_pts // per_line + 1) * line_len
+        # lattice scaling and the cell volume come first here: the division is fused
+        # into the conversion (io/vasp.py:140-149 does it afterwards; same operands)
+        if scale.shape[0] == 1:
+            lattice *= scale[0]
+        else:
+            for i in range(3):
+                lattice[i] *= scale[i]
+        lattice_vol = np.dot(lattice[0], np.cross(*lattice[1:]))
+        shape = tuple(int(g) for g in grid)
+
+        def block(pos):
+            f.seek(pos)
+            start, end, buf = _read_block(f, grid_pts, est)
+            try:
+                arr, used = parse_block(buf, shape, True, OP_DIVIDE, float(lattice_vol), device)
+            except ValueError:
+                if start + buf.size >= end:
+                    raise
+                f.seek(start)                              # variable-width lines: take the rest
+                buf = np.fromfile(f, dtype=np.uint8)
+                arr, used = parse_block(buf, shape, True, OP_DIVIDE, float(lattice_vol), device)
+            return arr, start + used
+
+        charge_end = None
+        if charge_flag:
+            density['charge'], charge_end = block(charge_pos)
+        if spin_flag:
+            # the spin block follows the augmentation occupancies, behind a second
+            # copy of the grid line (io/vasp.py:106-123 looks for it from mid-file)
+            f.seek(charge_end if charge_end is not None else charge_pos + est - line_len)
+            rest_pos = f.tell()
+            tail = f.read()
+            key = grid_line.strip()
+            hit, at = -1, 0
+            while True:
+                nl = tail.find(b'\n', at)
+                if nl < 0:
+                    break
+                if tail[at:nl].strip() == key and at > 0:
+                    hit = nl + 1
+                    break
+                at = nl + 1
+            del tail
+            if hit < 0:
+                print(f"  No spin density in {fn}")
+                spin_flag = False
+            else:
+                density['spin'], _ = block(rest_pos + hit)
+        print(f"  File {fn} closed. ", end='')
+    atoms = np.dot(atoms, lattice)
+    print(f"Time taken: {time() - t0:0.3f}s", end='\n\n')
+    try:
+        from pybader.io.vasp import write          # the reference's writer, when it is installed
+    except Exception:                              # noqa: BLE001
+        write = None
+    file_info = {
+        'filename': filename,
+        'prefix': prefix,
+        'file_type': 'VASP',
+        'buffer_size': buffer_size,
+        'write_function': write,
+        'element_nums': atom_nums,
+        'charge_flag': charge_flag,
+        'spin_flag': spin_flag,
+        'voxel_offset': np.zeros(3)
+    }
+    if atom_types is not None:
+        file_info['elements'] = atom_types
+    return density, lattice, atoms, file_info
