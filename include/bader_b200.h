@@ -236,6 +236,12 @@ int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_value
                    int64_t ny, int64_t nz, int x_fastest, int op, double operand, double *out,
                    int64_t *tokens_found, int64_t *bytes_consumed, int64_t *n_fallback,
                    int64_t *fallback, int64_t fallback_cap);
+/* bdr_parse_text keeps its device buffers between calls; this frees them     */
+int bdr_parse_release(int device);
+/* page-locked host memory for the readers' text and result buffers (numpy's
+ * pageable arrays cross PCIe at a fifth of the rate); NULL on failure         */
+void *bdr_host_alloc(int64_t bytes);
+int bdr_host_free(void *ptr);
 /* the same conversion for one token on the CPU (tests; no device needed):
  * 0 converted, 2 not handled exactly (ask strtod)                             */
 int bdr_parse_token_host(const char *token, int64_t len, double *out);

@@ -7,6 +7,7 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <mutex>
 
 namespace bdr {
 thread_local std::string g_err;
@@ -1481,6 +1482,51 @@ int bdr_run(bdr_ctx *c, const double *host_density, double vac_tol, double voxel
 }
 
 // ---- text -> grid --------------------------------------
+struct ParsePool {
+    void *p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaError_t reserve(int i, size_t bytes) {
+        if (cap[i] >= bytes) return cudaSuccess;
+        if (p[i]) cudaFree(p[i]);
+        p[i] = nullptr;
+        cap[i] = 0;
+        const cudaError_t e = cudaMalloc(&p[i], bytes);
+        if (e == cudaSuccess) cap[i] = bytes;
+        return e;
+    }
+    void release() {
+        for (int i = 0; i < 8; ++i) {
+            if (p[i]) cudaFree(p[i]);
+            p[i] = nullptr;
+            cap[i] = 0;
+        }
+    }
+};
+static ParsePool &parse_pool(int device) {
+    static ParsePool pools[64];
+    return pools[device & 63];
+}
+
+int bdr_parse_release(int device) {
+    CU(cudaSetDevice(device));
+    parse_pool(device).release();
+    return 0;
+}
+
+// page-locked host memory for the readers (text in, grid out): PCIe at full rate
+void *bdr_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail_msg("bdr_host_alloc: cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+int bdr_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return 0;
+}
+
 int bdr_parse_token_host(const char *token, int64_t len, double *out) {
     if (!token || !out || len <= 0) return fail_msg("bdr_parse_token_host: bad argument");
     int l = 0;
@@ -1498,21 +1544,20 @@ int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_value
     CU(cudaSetDevice(device));
     cudaStream_t st;
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const bool dbg = getenv("BDR_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(
+                        std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     const int64_t CHUNK = 256LL << 20;
     const int64_t cbytes = std::min<int64_t>(std::max<int64_t>(nbytes, 1), CHUNK);
     const int64_t max_blocks = (cbytes + TOK_BLOCK - 1) / TOK_BLOCK;
-    char *d_text = nullptr;
-    double *d_vals = nullptr, *d_out = nullptr;
-    unsigned *d_counts = nullptr, *d_tot1 = nullptr, *d_tot2 = nullptr;
-    ParseOut *d_po = nullptr;
-    int64_t *d_fb = nullptr;
+    // device buffers are kept between calls (a file is several blocks; cudaMalloc / cudaFree
+    // of gigabytes cost more than the conversion); bdr_parse_release frees them
+    static std::mutex pool_mutex;
+    std::lock_guard<std::mutex> pool_lock(pool_mutex);
+    ParsePool &pool = parse_pool(device);
     const int64_t fb_cap = std::max<int64_t>(fallback_cap, 0);
-    auto cleanup = [&]() {
-        for (void *p : {(void *)d_text, (void *)d_vals, (void *)d_out, (void *)d_counts, (void *)d_tot1,
-                        (void *)d_tot2, (void *)d_po, (void *)d_fb})
-            if (p) cudaFree(p);
-        cudaStreamDestroy(st);
-    };
+    auto cleanup = [&]() { cudaStreamDestroy(st); };
 #define PCU(x)                                                    \
     do {                                                          \
         cudaError_t e_ = (x);                                     \
@@ -1521,18 +1566,24 @@ int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_value
             return bdr::fail(#x, __FILE__, __LINE__, e_);         \
         }                                                         \
     } while (0)
-    PCU(cudaMalloc((void **)&d_text, (size_t)cbytes + 64));
-    PCU(cudaMalloc((void **)&d_vals, (size_t)n_values * sizeof(double)));
-    PCU(cudaMalloc((void **)&d_out, (size_t)n_values * sizeof(double)));
-    PCU(cudaMalloc((void **)&d_counts, (size_t)max_blocks * sizeof(unsigned)));
-    PCU(cudaMalloc((void **)&d_tot1, 1024 * sizeof(unsigned)));
-    PCU(cudaMalloc((void **)&d_tot2, 1024 * sizeof(unsigned)));
-    PCU(cudaMalloc((void **)&d_po, sizeof(ParseOut)));
-    PCU(cudaMalloc((void **)&d_fb, (size_t)std::max<int64_t>(fb_cap, 1) * 3 * sizeof(int64_t)));
+    PCU(pool.reserve(0, (size_t)cbytes + 64));
+    PCU(pool.reserve(1, (size_t)n_values * sizeof(double)));
+    PCU(pool.reserve(2, (size_t)n_values * sizeof(double)));
+    PCU(pool.reserve(3, (size_t)max_blocks * sizeof(unsigned)));
+    PCU(pool.reserve(4, 1024 * sizeof(unsigned)));
+    PCU(pool.reserve(5, 1024 * sizeof(unsigned)));
+    PCU(pool.reserve(6, sizeof(ParseOut)));
+    PCU(pool.reserve(7, (size_t)std::max<int64_t>(fb_cap, 1) * 3 * sizeof(int64_t)));
+    char *d_text = (char *)pool.p[0];
+    double *d_vals = (double *)pool.p[1], *d_out = (double *)pool.p[2];
+    unsigned *d_counts = (unsigned *)pool.p[3], *d_tot1 = (unsigned *)pool.p[4], *d_tot2 = (unsigned *)pool.p[5];
+    ParseOut *d_po = (ParseOut *)pool.p[6];
+    int64_t *d_fb = (int64_t *)pool.p[7];
     PCU(cudaMemsetAsync(d_po, 0, sizeof(ParseOut), st));
     // values no token reaches read as NaN
     PCU(cudaMemsetAsync(d_vals, 0xff, (size_t)n_values * sizeof(double), st));
     int64_t pos = 0, tokens = 0;
+    const double t_alloc = now();
     while (pos < nbytes && tokens < n_values) {
         // a chunk ends on whitespace, so no token straddles two chunks
         int64_t end = std::min(nbytes, pos + CHUNK);
@@ -1564,6 +1615,7 @@ int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_value
     ParseOut po;
     PCU(cudaMemcpyAsync(&po, d_po, sizeof(ParseOut), cudaMemcpyDeviceToHost, st));
     PCU(cudaStreamSynchronize(st));
+    const double t_parsed = now();
     const int64_t found = std::min(tokens, n_values);
     if (tokens_found) *tokens_found = found;
     if (bytes_consumed) *bytes_consumed = tokens >= n_values ? (int64_t)po.end_of_last : nbytes;
@@ -1579,10 +1631,18 @@ int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_value
         k_grid_finish<<<148 * 8, 256, 0, st>>>(d_vals, d_out, (int)nx, (int)ny, (int)nz, 0, op, operand);
     }
     PCU(cudaGetLastError());
+    PCU(cudaStreamSynchronize(st));
+    const double t_fin = now();
     PCU(cudaMemcpyAsync(out, d_out, (size_t)n_values * sizeof(double), cudaMemcpyDeviceToHost, st));
     PCU(cudaStreamSynchronize(st));
+    const double t_d2h = now();
 #undef PCU
     cleanup();
+    if (dbg)
+        fprintf(stderr, "[bdr] parse_text: %lld values from %.1f MB: alloc %.1f ms, H2D + tokenise + convert %.1f ms, "
+                "layout %.2f ms, D2H %.1f ms, free %.1f ms; %lld tokens for the host\n",
+                (long long)n_values, nbytes / 1e6, t_alloc - t_begin, t_parsed - t_alloc, t_fin - t_parsed,
+                t_d2h - t_fin, now() - t_d2h, (long long)po.n_fallback);
     return 0;
 }
 
