@@ -4,7 +4,7 @@ occupancies + spin block, with tiny / negative / zero values) and cube files,
 read by the REAL reference readers (pybader.io.vasp.read / pybader.io.cube.read,
 imported from /root/reference) and stored next to the text files.
 
-    HOME=/tmp/x PYTHONPATH=/root/reference python tests/golden/make_io_golden.py
+    HOME=/tmp/x PYTHONPATH=/root/reference python tests/golden_io/make_io_golden.py
 """
 import contextlib
 import io

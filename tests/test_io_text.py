@@ -1,6 +1,6 @@
 """Text readers: the decimal -> double conversion on the CPU
 against Python's float(), and the GPU readers against fixtures produced by the real
-reference readers (tests/golden/make_io_golden.py)."""
+reference readers (tests/golden_io/make_io_golden.py)."""
 import ctypes
 import os
 
@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+GOLDEN = os.path.join(ROOT, 'tests', 'golden_io')
 
 
 @pytest.fixture(scope='module')
