@@ -65,6 +65,22 @@ for name, k in sorted(b['kernels'].items(), key=lambda kv: -kv[1]['ms_per_step']
       f"{k.get('achieved_gbs', 0):.0f} | {k.get('frac', 0):.3f} | {dr / 1e9:.2f} | {algb:.2f} |")
 w(f"\nSum of the families: {sum(k['ms_per_step'] for k in b['kernels'].values()):.2f} ms of the {b['ms_per_step']:.2f} ms step; "
   "the rest is host round trips between data-dependent launches (counter read-backs).\n")
+w("## Scaling (weak: 2^30 voxels per GPU; x-slabs, NCCL + NVLink peer loads)\n")
+w("| GPUs | grid | ms / step | Gvoxel/s | e2e Gvoxel/s | kernels on rank 0, ms | note |")
+w("|---|---|---|---|---|---|---|")
+w(f"| 1 | 1024³ | {b['ms_per_step']:.2f} | {b['value'] / 1e9:.1f} | {b['e2e']['value'] / 1e9:.2f} | "
+  f"{sum(k['ms_per_step'] for k in b['kernels'].values()):.1f} | refine ('changed', 2) |")
+for n in (2, 4, 8):
+    f = os.path.join(P, f'{tag}_bench_n{n}.json')
+    if not os.path.exists(f):
+        continue
+    d = load(f'{tag}_bench_n{n}.json')
+    w(f"| {n} | {d['config']['workload'].split(' ')[0]} | {d['ms_per_step']:.2f} | {d['value'] / 1e9:.1f} | "
+      f"{d['e2e']['value'] / 1e9:.2f} | {sum(k['ms_per_step'] for k in d['kernels'].values()):.1f} | "
+      f"refine ('all', 2): one more full edge pass + trace than N = 1; {d.get('neargrid_passes')} rounds, "
+      f"{d.get('exit_rounds')} exit rounds |")
+w("\nThe N > 1 step is a heavier algorithm than the N = 1 step (DESIGN.md section 7) and is driven from Python "
+  "with an all-reduce per round; the gap between the kernel sum and the step is that protocol.\n")
 w("## Files\n")
 for f in sorted(os.listdir(P)):
     if f == 'README.md':
@@ -73,7 +89,8 @@ for f in sorted(os.listdir(P)):
             'launches_1024.csv': "ncu launch list (gpu__time_duration.sum) of `bench.py --steps 1 --warmup 3`",
             'traffic.json': "DRAM bytes and duration of every launch of one step (tools/ncu_traffic.py)",
             'ncu_set_full_1024.txt': "key metrics of the `--set full` captures of the top kernels (tools/ncu_summary.py)",
-            'pytest_gpu.log': "`pytest -m gpu` on the box", 'smoke.log': "`__graft_entry__.smoke()`"}
+            'pytest_gpu.log': "`pytest -m gpu` on the box", 'smoke.log': "`__graft_entry__.smoke()`",
+            'io_bench_256.json': "tools/io_bench.py: CHGCAR reader (GPU text -> grid) next to the reference's conversion"}
     desc = next((v for k, v in what.items() if f.endswith(k)), '')
     if '_bench_n' in f:
         desc = "bench.py line under torchrun, N = " + f.split('_bench_n')[1].split('.')[0]
