@@ -90,6 +90,8 @@ for f in sorted(os.listdir(P)):
             'traffic.json': "DRAM bytes and duration of every launch of one step (tools/ncu_traffic.py)",
             'ncu_set_full_1024.txt': "key metrics of the `--set full` captures of the top kernels (tools/ncu_summary.py)",
             'pytest_gpu.log': "`pytest -m gpu` on the box", 'smoke.log': "`__graft_entry__.smoke()`",
+            'sanitizer_memcheck.log': "compute-sanitizer memcheck over smoke(): 0 errors",
+            'sanitizer_racecheck.log': "compute-sanitizer racecheck over smoke(): the intended in-tile chase race only (DESIGN.md section 8)",
             'io_bench_256.json': "tools/io_bench.py: CHGCAR reader (GPU text -> grid) next to the reference's conversion"}
     desc = next((v for k, v in what.items() if f.endswith(k)), '')
     if '_bench_n' in f:
