@@ -73,7 +73,6 @@ k_scan_add(unsigned *v, int64_t n, const unsigned *__restrict__ totals_scanned) 
 struct ParseOut {
     unsigned long long n_fallback;   // tokens handed to the host
     unsigned long long end_of_last;  // byte offset (in the whole text) just past token n_values - 1
-    unsigned long long chunk_tokens; // tokens of this chunk (written by the last block)
 };
 
 __global__ void __launch_bounds__(256)
