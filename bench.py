@@ -69,12 +69,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.active = True      # rows are kept only while a timed region runs
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                 '--format=csv,noheader,nounits', '-lms', '200'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -83,7 +84,8 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            if self.active:
+                self.rows.append([x.strip() for x in line.split(',')])
 
     def stop(self):
         if not self.proc:
@@ -338,7 +340,7 @@ def main():
     prof = e.profile_get()
     tsteps, tvox = e.trace_steps()
     e.profile(False)
-    clock_info = clocks.stop()
+    clocks.active = False
     ms_per_step = total_ms / args.steps
     value = N / (ms_per_step * 1e-3)
 
@@ -360,17 +362,20 @@ def main():
         e.run(host_rho, None, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
               want_sums=False, out_labels=host_lab)
         e.synchronize()
+        clocks.active = True
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e.run(host_rho, None, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
                   want_sums=False, out_labels=host_lab)
         e.synchronize()
         dt = (time.perf_counter() - t0) / args.steps
+        clocks.active = False
         e2e = {"value": N / dt, "unit": UNIT, "h2d_bytes_per_step": N * 8,
                "d2h_bytes_per_step": N * ldt.itemsize + n_max * 24, "ms_per_step": dt * 1e3,
                "api": "bdr_run (C ABI, pinned host density in, narrowed labels + maxima out)"}
         del host_rho, host_lab
 
+    clock_info = clocks.stop()      # sampled through both timed regions (device steps and e2e)
     cpu = None if args.no_cpu else cpu_baseline_leg(args.cpu_sample)
     e.close()
     out = {
