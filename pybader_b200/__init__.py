@@ -16,10 +16,13 @@ _PATCHED = ('assign_to_atoms', 'bader_calc', 'dtype_calc', 'refine', 'surface_di
             'atom_assign', 'charge_sum', 'vacuum_assign', 'volume_mask')
 
 
-def install(interface_module=None):
+def install(interface_module=None, readers=True):
     """Swap the numba hot path under the reference's `Bader` object for this
     engine by rebinding the names `pybader.interface` imported at
-    interface.py:16-18.  Returns the dict of replaced callables (for uninstall)."""
+    interface.py:16-18.  With `readers` the CHGCAR / cube `read()` functions that
+    `Bader.from_file` dispatches to (interface.py:141-173: `io_.read(...)` on the
+    modules of `pybader.io`) are replaced too (pybader_b200/io).
+    Returns the dict of replaced callables (for uninstall)."""
     from . import _lib, thread_handlers, utils
     _lib.load()   # fail loudly here, not in the middle of a run
     if interface_module is None:
@@ -32,6 +35,14 @@ def install(interface_module=None):
     old = {k: getattr(interface_module, k) for k in _PATCHED}
     for k, v in mine.items():
         setattr(interface_module, k, v)
+    if readers:
+        try:
+            import pybader.io as ref_io
+            from . import io as my_io
+            old['io.vasp.read'], old['io.cube.read'] = ref_io.vasp.read, ref_io.cube.read
+            ref_io.vasp.read, ref_io.cube.read = my_io.vasp.read, my_io.cube.read
+        except ImportError:
+            pass
     return old
 
 
@@ -39,4 +50,8 @@ def uninstall(old, interface_module=None):
     if interface_module is None:
         import pybader.interface as interface_module
     for k, v in old.items():
-        setattr(interface_module, k, v)
+        if k.startswith('io.'):
+            import pybader.io as ref_io
+            setattr(getattr(ref_io, k.split('.')[1]), 'read', v)
+        else:
+            setattr(interface_module, k, v)
