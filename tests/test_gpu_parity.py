@@ -353,7 +353,7 @@ def test_noisy_density_many_small_volumes(th, ut, orc, noise):
     volumes (outside the BASELINE configs, which are smooth): ongrid stays bit-exact;
     neargrid finds the same maxima, and with both sides refined to convergence
     (('all', -1): on such data the reference is still moving after 2 iterations) the
-    labels agree on >= 99 % of the voxels"""
+    labels agree on >= 99.9 % of the voxels"""
     from pybader_b200 import geometry as geo, synth
     c = synth.case_c1(40)
     rho, _ = synth.make(c)
@@ -375,8 +375,7 @@ def test_noisy_density_many_small_volumes(th, ut, orc, noise):
     key = lambda m: sorted(map(tuple, m.tolist()))
     assert key(mx) == key(rmx)
     ndiff = int((canonical(vol, mx) != canonical(rvol, rmx)).sum())
-    if ndiff > 0.01 * vol.size:     # informational outside the BASELINE configs: report, do not gate
-        pytest.skip(f"{s['name']}: {ndiff} of {vol.size} voxels differ after convergence on both sides")
+    assert ndiff <= 1e-3 * vol.size      # measured on B200: 7 and 5 of 64,000
     print(f"{s['name']}: {mx.shape[0]} maxima, {ndiff} of {vol.size} voxels differ from the reference path")
 
 
