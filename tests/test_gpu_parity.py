@@ -346,6 +346,29 @@ def test_edge_pass_equality_bits_match_minmax_kernel(shape, monkeypatch):
         np.testing.assert_array_equal(out[0][1], out[1][1])
 
 
+# ------------------------------ bader-read's re-threshold flow ----
+def test_rethreshold_labelled_volumes(th, ut, orc, seeded):
+    """entry_points.py:238-255: a finished run is re-thresholded with a larger vacuum_tol,
+    `volumes_init(volumes=bader_volumes)` + `sum_volumes`: vacuum_assign on an array that
+    already holds labels, then charge_sum -- identical to the oracle"""
+    s = seeded
+    _, vol = th.bader_calc('ongrid', s['rho'], gpu_fresh(ut, s), s['dist_mat'], s['T_grad'], 1)
+    n = int(vol.max()) + 1
+    tol = float(np.quantile(s['rho'], 0.35))
+    a, b = vol.copy(), vol.copy()
+    ra, rq, rv = orc.vacuum_assign(s['rho'], a, tol, s['rho'], s['voxel_volume'])
+    gb, gq, gv = ut.vacuum_assign(s['rho'], b, tol, s['rho'], s['voxel_volume'])
+    assert gb.dtype == vol.dtype
+    np.testing.assert_array_equal(gb, ra)
+    assert (gb == -1).sum() >= (vol == -1).sum() and (gb == -1).sum() >= 0.3 * gb.size
+    assert gq == pytest.approx(rq, rel=1e-12) and gv == pytest.approx(rv, rel=1e-12)
+    q, v, oq, ov = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    ut.charge_sum(q, v, s['voxel_volume'], s['rho'], gb)
+    orc.charge_sum(oq, ov, s['voxel_volume'], s['rho'], ra)
+    np.testing.assert_allclose(q, oq, rtol=1e-12)
+    np.testing.assert_allclose(v, ov, rtol=1e-12)
+
+
 # ------------------------------------------------------- noisy densities ----
 @pytest.mark.parametrize('noise', [1.0, 3.0])
 def test_noisy_density_many_small_volumes(th, ut, orc, noise):
