@@ -1,0 +1,89 @@
+"""numpy restatements of the two reformulations the CUDA path relies on, checked on the
+CPU against the plain definitions (the kernels themselves are checked on the GPU):
+
+* csrc/edge.cuh -- the label half of refinement.edge_find through equality bits:
+  "27 labels all equal" as an AND of 26 adjacent-pair equalities, voxels with vacuum in
+  reach classified by the definition;
+* csrc/seed.cuh -- the fp32 "clearly uphill" acceptance rule implies the reference's exact
+  fp64 ongrid criterion (rho_n - rho_c) * w + rho_c > rho_c for the accepted neighbour.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+OFFS = [d for d in itertools.product((-1, 0, 1), repeat=3)]
+
+
+def edge_candidates_definition(lab):
+    """refinement.py:339-376 (label half): non-vacuum voxel with a non-vacuum neighbour of
+    another label; vacuum neighbours are ignored"""
+    out = np.zeros(lab.shape, dtype=bool)
+    for d in OFFS:
+        nb = np.roll(lab, tuple(-x for x in d), axis=(0, 1, 2))
+        out |= (nb != -1) & (nb != lab)
+    return out & (lab != -1)
+
+
+def edge_candidates_eqbits(lab):
+    """the formulation of csrc/edge.cuh"""
+    eqz = lab == np.roll(lab, -1, axis=2)
+    eqy = lab == np.roll(lab, -1, axis=1)
+    eqx = lab == np.roll(lab, -1, axis=0)
+    vac = lab == -1
+    # per plane: the 3 x 3 (y, z) patch around (y, z) is uniform
+    zrow = eqz & np.roll(eqz, 1, axis=2)                      # L[z-1] == L[z] == L[z+1]
+    P = zrow & np.roll(zrow, 1, axis=1) & np.roll(zrow, -1, axis=1)
+    P &= eqy & np.roll(eqy, 1, axis=1)                        # rows y-1, y, y+1 joined at column z
+    uniform = P & np.roll(P, 1, axis=0) & np.roll(P, -1, axis=0) & eqx & np.roll(eqx, 1, axis=0)
+    cand = ~uniform & ~vac
+    # vacuum within Chebyshev distance 1: the chain argument does not apply there
+    vnear = np.zeros(lab.shape, dtype=bool)
+    for d in OFFS:
+        vnear |= np.roll(vac, d, axis=(0, 1, 2))
+    deferred = cand & vnear
+    cand &= ~deferred
+    cand[deferred] = edge_candidates_definition(lab)[deferred]   # k_edge_deferred: by definition
+    return cand, int(deferred.sum())
+
+
+@pytest.mark.parametrize('shape,vacuum', [((9, 7, 40), False), ((12, 5, 33), True), ((3, 3, 3), True),
+                                          ((2, 6, 70), False), ((16, 16, 16), True)])
+def test_equality_bits_equal_definition(shape, vacuum):
+    rng = np.random.default_rng(sum(shape))
+    coarse = rng.integers(0, 4, size=tuple((n + 3) // 4 for n in shape))
+    lab = np.kron(coarse, np.ones((4, 4, 4), dtype=np.int64))[:shape[0], :shape[1], :shape[2]].copy()
+    if vacuum:
+        lab[rng.random(shape) < 0.08] = -1
+        lab[:, :, shape[2] // 2] = -1
+    got, n_def = edge_candidates_eqbits(lab)
+    np.testing.assert_array_equal(got, edge_candidates_definition(lab))
+    assert (n_def > 0) == vacuum
+
+
+def test_fp32_clearly_uphill_implies_exact_uphill():
+    """seed.cuh accepts pair winner k when (max(f32(rho_a), f32(rho_b)) - f32(rho_c)) * w_k is at
+    least |f32(rho_c)| * 2^-21 * w_max (and above an absolute floor); for that neighbour the
+    exact fp64 expression of methods.py:110-112 must exceed rho_c"""
+    rng = np.random.default_rng(11)
+    w = rng.uniform(0.5, 60.0, 13)
+    wmax = w.max()
+    c1 = np.float32(2.0 ** -21 * wmax * 1.0001)
+    floor = np.float32(2.0 ** -96 * wmax)
+    n = 400000
+    for scale in (1.0, 1e-8, 1e-30, 1e12):
+        rc = rng.lognormal(0, 2, n) * scale
+        # neighbours from far below to a hair above the centre, incl. fp32-invisible differences
+        rel = rng.choice([1e-16, 1e-12, 1e-9, 3e-8, 1e-7, 3e-7, 1e-6, 1e-3, 0.3], n) * rng.choice([-1, 1], n)
+        rn = rc * (1.0 + rel * rng.random(n))
+        k = rng.integers(0, 13, n)
+        with np.errstate(over='ignore', under='ignore'):
+            rcf, rnf = rc.astype(np.float32), rn.astype(np.float32)
+            score = (rnf - rcf) * w[k].astype(np.float32)
+            thr = np.maximum(np.abs(rcf) * c1, floor)
+        accept = score >= thr
+        exact = (rn - rc) * w[k] + rc            # numpy does not contract to FMA
+        assert np.all(exact[accept] > rc[accept])
+        assert np.all(rn[accept] > rc[accept])
+        if scale in (1.0, 1e12):
+            assert accept.sum() > 0.1 * n and (~accept).sum() > 0.1 * n
