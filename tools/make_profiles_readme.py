@@ -63,6 +63,33 @@ for name, k in sorted(b['kernels'].items(), key=lambda kv: -kv[1]['ms_per_step']
     w(f"| {name} | {', '.join('`%s`' % x for x in ks if x in tr['kernels']) or '—'} | {k['ms_per_step']:.2f} | "
       f"{k['launches_per_step']:.0f} | {alg if alg else '—'} | "
       f"{k.get('achieved_gbs', 0):.0f} | {k.get('frac', 0):.3f} | {dr / 1e9:.2f} | {algb:.2f} |")
+# share of the step per family: CUDA events (bench.py) vs the ncu launch list of the same command
+import csv as _csv
+rows = list(_csv.reader(open(os.path.join(P, f'{tag}_launches_1024.csv'))))
+h = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
+hdr = rows[h]
+kn, mv, mu = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+launches = []
+for r in rows[h + 1:]:
+    if len(r) > mv:
+        name = r[kn].replace('void ', '').split('(')[0].split('<')[0]
+        t = float(r[mv].replace(',', '')) * {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0}.get(r[mu][:2].rstrip('e'), 1e-6)
+        launches.append((name, t))
+first = [i for i, (n_, _) in enumerate(launches) if n_ in ('k_seed_pointers', 'k_ongrid_pointers')]
+last = launches[first[-1]:]                      # the timed step (the last one of the run)
+k2f = {k: f for f, ks in fam_k.items() for k in ks}
+ncu_ms = {}
+for n_, t in last:
+    f = k2f.get(n_)
+    if f:
+        ncu_ms[f] = ncu_ms.get(f, 0.0) + t
+tot_ncu, tot_ev = sum(ncu_ms.values()), sum(k['ms_per_step'] for k in b['kernels'].values())
+w("\nShare of the step, CUDA events in bench.py vs the ncu launch list of the same command "
+  f"(`{tag}_launches_1024.csv`, last step; ncu serialises launches and runs them cold, so only shares compare):\n")
+w("| family | events ms | events share | ncu ms | ncu share |\n|---|---|---|---|---|")
+for name, k in sorted(b['kernels'].items(), key=lambda kv: -kv[1]['ms_per_step']):
+    w(f"| {name} | {k['ms_per_step']:.2f} | {k['ms_per_step'] / tot_ev:.3f} | {ncu_ms.get(name, 0):.2f} | "
+      f"{ncu_ms.get(name, 0) / tot_ncu:.3f} |")
 w(f"\nSum of the families: {sum(k['ms_per_step'] for k in b['kernels'].values()):.2f} ms of the {b['ms_per_step']:.2f} ms step; "
   "the rest is host round trips between data-dependent launches (counter read-backs).\n")
 w("## Scaling (weak: 2^30 voxels per GPU; x-slabs, NCCL + NVLink peer loads)\n")
