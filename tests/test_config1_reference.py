@@ -1,4 +1,4 @@
-"""BASELINE config 1 at full size against the REAL reference: tests/golden_c1/c1_96.npz holds
+"""BASELINE configs 1 and 2 at full size against the REAL reference: tests/golden_c1/*.npz hold
 what pybader's numba kernels returned for the 96^3 three-atom cell (make_c1_golden.py).
 The density is regenerated and must hash to the stored value, else these tests skip."""
 import hashlib
@@ -65,3 +65,39 @@ def test_cuda_path_equals_reference_at_full_size(c1):
     np.testing.assert_allclose(v, g['volume'], rtol=1e-6)
     print(f"config 1 vs the reference itself: {int((vol != g['neargrid_refined_labels']).sum())} "
           f"of {vol.size} voxels differ")
+
+
+# ---------------------------------------------------------------- config 2 ----
+@pytest.fixture(scope='module')
+def c2():
+    from pybader_b200 import geometry as geo, synth
+    g = np.load(os.path.join(ROOT, 'tests', 'golden_c1', 'c2_256.npz'))
+    c = synth.case_rocksalt(256, cells=4, offset=0.13)
+    tx, ty, tz = synth.separable_tables(c)
+    rho = np.ascontiguousarray(np.einsum('ai,aj,ak->ijk', tx, ty, tz, optimize=True))
+    if hashlib.sha256(rho.tobytes()).digest() != g['rho_sha256'].tobytes():
+        pytest.skip("this CPU does not reproduce the stored density bit for bit")
+    return dict(g=g, rho=rho, dist=geo.distance_matrix(c['lattice'], rho.shape),
+                T=geo.T_grad(c['lattice'], rho.shape))
+
+
+def test_oracle_equals_reference_config2(c2):
+    """BASELINE config 2 (256^3 rocksalt-like cell, 64 maxima, method=ongrid): the oracle
+    against the real reference's maxima list and labels, bit for bit"""
+    from oracle import pyoracle as orc
+    g, rho = c2['g'], c2['rho']
+    mx, vol = orc.bader_calc('ongrid', rho, np.zeros(rho.shape, np.int32), c2['dist'], c2['T'])
+    np.testing.assert_array_equal(mx, g['ongrid_maxima'])
+    assert vol.dtype == g['ongrid_labels'].dtype
+    np.testing.assert_array_equal(vol, g['ongrid_labels'])
+
+
+@pytest.mark.gpu
+def test_cuda_path_equals_reference_config2(c2):
+    """the CUDA ongrid path against the real reference's output at 256^3: bit-exact"""
+    from pybader_b200 import thread_handlers as th
+    g, rho = c2['g'], c2['rho']
+    mx, vol = th.bader_calc('ongrid', rho, np.zeros(rho.shape, np.int32), c2['dist'], c2['T'], 1)
+    np.testing.assert_array_equal(mx, g['ongrid_maxima'])
+    assert vol.dtype == g['ongrid_labels'].dtype
+    np.testing.assert_array_equal(vol, g['ongrid_labels'])
