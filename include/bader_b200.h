@@ -236,6 +236,14 @@ int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_value
                    int64_t ny, int64_t nz, int x_fastest, int op, double operand, double *out,
                    int64_t *tokens_found, int64_t *bytes_consumed, int64_t *n_fallback,
                    int64_t *fallback, int64_t fallback_cap);
+/* grid -> text: appends the numeric block of a CHGCAR (io/vasp.py:245-258) or of a
+ * cube file (io/cube.py:215-222) to `path`, formatted like utils.python_format
+ * (utils.py:85-94): every value " %.{prec}E" (sign_space: " % .{prec}E"), per_line
+ * values per line, a line break at the end of every row of row_len values.
+ * data is C order [nx][ny][nz]; x_fastest writes it in CHGCAR order (x fastest) as one
+ * row of nx*ny*nz values.  Host code on all host threads (no device needed).      */
+int bdr_format_grid(const char *path, const double *data, int64_t nx, int64_t ny, int64_t nz,
+                    int x_fastest, int64_t row_len, int per_line, int prec, int sign_space);
 /* bdr_parse_text keeps its device buffers between calls; this frees them     */
 int bdr_parse_release(int device);
 /* page-locked host memory for the readers' text and result buffers (numpy's

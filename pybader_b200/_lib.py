@@ -69,6 +69,7 @@ SIGNATURES = {
                         ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64), _p, _i64], _int),
     "bdr_parse_token_host": ([ctypes.c_char_p, _i64, ctypes.POINTER(_f64)], _int),
     "bdr_parse_release": ([_int], _int),
+    "bdr_format_grid": ([ctypes.c_char_p, _p, _i64, _i64, _i64, _int, _i64, _int, _int, _int], _int),
     "bdr_host_alloc": ([_i64], _p),
     "bdr_host_free": ([_p], _int),
 }

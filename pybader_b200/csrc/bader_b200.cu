@@ -4,6 +4,7 @@
 #include "seed.cuh"
 #include "edge.cuh"
 #include "parse.cuh"
+#include "format.h"
 
 #include <chrono>
 #include <cstdlib>
@@ -1643,6 +1644,15 @@ int bdr_parse_text(int device, const char *text, int64_t nbytes, int64_t n_value
                 "layout %.2f ms, D2H %.1f ms, free %.1f ms; %lld tokens for the host\n",
                 (long long)n_values, nbytes / 1e6, t_alloc - t_begin, t_parsed - t_alloc, t_fin - t_parsed,
                 t_d2h - t_fin, now() - t_d2h, (long long)po.n_fallback);
+    return 0;
+}
+
+int bdr_format_grid(const char *path, const double *data, int64_t nx, int64_t ny, int64_t nz,
+                    int x_fastest, int64_t row_len, int per_line, int prec, int sign_space) {
+    if (!path || !data) return fail_msg("bdr_format_grid: bad argument");
+    std::string err;
+    if (format_grid_append(path, data, nx, ny, nz, x_fastest, row_len, per_line, prec, sign_space, &err))
+        return fail_msg(err);
     return 0;
 }
 

@@ -86,10 +86,6 @@ def read(fn, orbitals=0, device=0):
     atoms *= bohr_to_ang
     if nval > 1:
         density['charge'] *= ang_to_bohr**3
-    try:
-        from pybader.io.cube import write
-    except Exception:                              # noqa: BLE001
-        write = None
     file_info = {
         'filename': fn,
         'prefix': prefix,
@@ -99,3 +95,50 @@ def read(fn, orbitals=0, device=0):
         'voxel_offset': np.array([.5, .5, .5])
     }
     return density, lattice, atoms, file_info
+
+
+def write(fn, atoms, lattice, density, file_info, prefix=None, suffix='.cube'):
+    """Write a cube style charge density (io/cube.py:159-222): same arguments, same file.
+    Like the reference, `atoms`, `lattice` and the charge array are converted to Bohr
+    units IN PLACE (io/cube.py:183-187)."""
+    from ._format import append_block, fortran_lines
+    if prefix is not None:
+        fn = prefix + fn
+    fn += suffix
+    fmt = file_info.get('fortran_format', 0)
+    charge = density['charge']
+    atoms *= ang_to_bohr
+    charge *= bohr_to_ang**3
+    lattice *= ang_to_bohr
+    lattice /= charge.shape
+    lattice_width = np.max(np.log10(np.abs(lattice[lattice != 0]))) + 9
+    lattice_width = max([int(lattice_width), 9]) + 1
+    lattice_prec = 17 - lattice_width
+    atoms_width = np.max(np.log10(np.abs(atoms[atoms != 0]))) + 9
+    atoms_width = max([int(atoms_width), 9]) + 1
+    atoms_prec = 17 - atoms_width
+    with open(fn, 'w') as f:
+        f.write("Cube File writen in pybader\n")
+        f.write(file_info['comment'])
+        f.write(f"{atoms.shape[0]:>5}{'  0.0000000'*3}\n")
+        for i, lat in enumerate(lattice):
+            x, y, z = lat
+            f.write(f"{charge.shape[i]:>5}")
+            f.write(f" {x:> {10}.{lattice_prec}f} {y:> {10}.{lattice_prec}f} {z:> {10}.{lattice_prec}f}\n")
+        for i, atom in enumerate(atoms):
+            x, y, z = atom
+            f.write(f"{file_info['elements'][i]:>5}")
+            f.write('  0.0000000')
+            f.write(f" {x:> {10}.{atoms_prec}f} {y:> {10}.{atoms_prec}f} {z:> {10}.{atoms_prec}f}\n")
+        if fmt == 2:
+            nz = charge.shape[2]
+            full = nz // 6 * 6
+            for i in range(charge.shape[0]):
+                for j in range(charge.shape[1]):
+                    row = charge[i, j]
+                    if full:
+                        f.write(fortran_lines(row[:full].reshape(-1, 6), 5))
+                    if full < nz:
+                        f.write(fortran_lines(row[full:].reshape(1, -1), 5))
+    if fmt != 2:
+        append_block(fn, charge, False, charge.shape[2], 6, 5, fmt == 1)

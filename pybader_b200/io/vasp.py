@@ -112,10 +112,6 @@ def read(fn, charge_flag=True, spin_flag=False, buffer_size=64, device=0):
         print(f"  File {fn} closed. ", end='')
     atoms = np.dot(atoms, lattice)
     print(f"Time taken: {time() - t0:0.3f}s", end='\n\n')
-    try:
-        from pybader.io.vasp import write          # the reference's writer, when it is installed
-    except Exception:                              # noqa: BLE001
-        write = None
     file_info = {
         'filename': filename,
         'prefix': prefix,
@@ -130,3 +126,59 @@ def read(fn, charge_flag=True, spin_flag=False, buffer_size=64, device=0):
     if atom_types is not None:
         file_info['elements'] = atom_types
     return density, lattice, atoms, file_info
+
+
+def write(fn, atoms, lattice, density, file_info, prefix='', suffix='-CHGCAR'):
+    """Write a VASP style charge density (io/vasp.py:167-258): same arguments, same file.
+
+    Like the reference, the density arrays are scaled by the cell volume IN PLACE
+    (io/vasp.py:188-190).  The number blocks are formatted natively (`bdr_format_grid`)
+    for fortran_format 0 and 1; 2 goes through the numpy restatement of
+    utils.fortran_format.  One deliberate difference: a grid whose size is a multiple of
+    5 is written correctly (the reference fails on `charge[:-0]`, io/vasp.py:202-203)."""
+    from ._format import append_block, fortran_lines
+    fn = prefix + fn + suffix
+    fmt = file_info.get('fortran_format', 0)
+    lattice_vol = np.dot(lattice[0], np.cross(*lattice[1:]))
+    for key in density:
+        density[key] *= lattice_vol
+    blocks = []
+    if file_info['charge_flag']:
+        blocks.append(density.get('charge'))
+    if file_info['spin_flag']:
+        blocks.append(density.get('spin'))
+    shape = blocks[0].shape
+    lattice_width = np.max(np.log10(np.abs(lattice[lattice != 0]))) + 9
+    lattice_width = max([int(lattice_width), 9]) + 1
+    lattice_prec = 17 - lattice_width
+    atoms_width = np.max(np.log10(np.abs(atoms))).astype(int) + 9
+    atoms_width = max([atoms_width, 9]) + 1
+    atoms_prec = 17 - atoms_width
+    with open(fn, 'w') as f:
+        f.write(file_info['comment'])
+        f.write(f"{1:0< 10.7f}\n")
+        for x, y, z in lattice:
+            f.write(f" {x:> {10}.{lattice_prec}f} {y:> {10}.{lattice_prec}f} {z:> {10}.{lattice_prec}f}\n")
+        if file_info.get('elements', None) is not None:
+            f.write('  '.join(file_info['elements']) + '\n')
+        f.write('  '.join(file_info['element_nums'].astype(str)) + '\n')
+        f.write('Cartesian\n')
+        for x, y, z in atoms:
+            f.write(f" {x:> {10}.{atoms_prec}f} {y:> {10}.{atoms_prec}f} {z:> {10}.{atoms_prec}f}\n")
+        f.write('\n')
+    x, y, z = shape
+    for block in blocks:
+        with open(fn, 'a') as f:
+            f.write(f" {x:>5} {y:>5} {z:>5}\n")
+        if fmt == 2:
+            flat = np.swapaxes(block, 0, -1).flatten()
+            full = flat.size // 5 * 5
+            with open(fn, 'a') as f:
+                if full:
+                    f.write(fortran_lines(flat[:full].reshape(-1, 5), 11))
+                if full < flat.size:
+                    f.write(fortran_lines(flat[full:].reshape(1, -1), 11))
+        else:
+            # file order is x fastest: one numpy transpose (as the reference does), then a single row
+            flat = np.ascontiguousarray(np.swapaxes(block, 0, -1)).reshape(1, 1, -1)
+            append_block(fn, flat, False, flat.size, 5, 11, fmt == 1)
