@@ -71,3 +71,27 @@ def test_chgcar_writer_grid_multiple_of_five(tmp_path):
     body = [ln for ln in body if ln]
     assert len(body) == 12 and all(len(ln.split()) == 5 for ln in body)
     assert len({len(ln) for ln in body}) == 1
+
+
+@pytest.mark.parametrize('prec,sign_space', [(11, False), (5, False), (11, True), (3, False)])
+def test_native_formatter_equals_python_format(prec, sign_space, tmp_path):
+    """bdr_format_grid against Python's own formatting (utils.python_format is
+    ' {:.{prec}E}' per value), over magnitudes that take the exact path and ones that fall
+    back to printf (huge, tiny, zero, negative zero, few-bit mantissas = exact decimal ties)"""
+    from pybader_b200.io._format import append_block
+    rng = np.random.default_rng(prec + 7 * sign_space)
+    n = 6 * 7 * 50
+    v = rng.lognormal(0, 6, n) * rng.choice([1, -1], n)
+    v[:200] = np.ldexp(1.0 + rng.integers(0, 16, 200) / 16.0, rng.integers(-40, 40, 200))
+    v[200:260] = rng.lognormal(0, 3, 60) * 1e15
+    v[260:320] = rng.lognormal(0, 3, 60) * 1e-120
+    v[320:324] = [0.0, -0.0, 5e-324, 1.7976931348623157e308]
+    a = v.reshape(6, 7, 50)
+    path = os.path.join(str(tmp_path), 'block.txt')
+    append_block(path, a, False, 50, 6, prec, sign_space)
+    align = ' ' if sign_space else ''
+    want = []
+    for row in a.reshape(-1, 50):
+        for k in range(0, 50, 6):
+            want.append(''.join(f' {x:{align}.{prec}E}' for x in row[k:k + 6]) + '\n')
+    assert open(path).read() == ''.join(want)
