@@ -15,7 +15,7 @@
 // are ignored by the reference (refinement.py:370-371), not compared -- and
 // are evaluated exactly from a small deferred list.
 // Result: the same ebits / vbits as the min/max kernel k_edge_bits (kernels.cuh),
-// at ~20 instead of ~67 issue slots per voxel.
+// at ~30 instead of ~67 issue slots per voxel (ncu).
 // Algorithmic traffic: R 4 (labels) + W 4/8 (four bit volumes) per voxel, then
 // R ~27/8 + W 1/8 per voxel for the word pass.
 #pragma once
