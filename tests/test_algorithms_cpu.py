@@ -87,3 +87,74 @@ def test_fp32_clearly_uphill_implies_exact_uphill():
         assert np.all(rn[accept] > rc[accept])
         if scale in (1.0, 1e12):
             assert accept.sum() > 0.1 * n and (~accept).sum() > 0.1 * n
+
+
+def seed_field_model(rho, dist_mat):
+    """numpy model of k_seed_pointers (csrc/seed.cuh): pairs k / 26-k scored in fp32 with the
+    index in the low mantissa bits, the winner accepted when clearly uphill, else the exact
+    fp64 argmax of methods.py:87-117 (tests/shard_model.ongrid_pointers)"""
+    from tests.shard_model import ongrid_pointers
+    offs = [d for d in itertools.product((-1, 0, 1), repeat=3)]
+    w = np.array([dist_mat[d] for d in offs])                   # negative indices: interface.py:249-258
+    wf = w[:13].astype(np.float32)
+    wmax = w[:13].max()
+    c1, floor = np.float32(2.0 ** -21 * wmax * 1.0001), np.float32(2.0 ** -96 * wmax)
+    rf = rho.astype(np.float32)
+    lin = np.arange(rho.size, dtype=np.int64).reshape(rho.shape)
+    best = np.zeros(rho.shape, dtype=np.float32)
+    for k in range(13):
+        a = np.roll(rf, tuple(-x for x in offs[k]), axis=(0, 1, 2))
+        b = np.roll(rf, tuple(-x for x in offs[26 - k]), axis=(0, 1, 2))
+        with np.errstate(over='ignore', under='ignore', invalid='ignore'):
+            s = (np.maximum(a, b) - rf) * wf[k]
+        tagged = ((s.view(np.uint32) & np.uint32(0xfffffff0)) | np.uint32(k)).view(np.float32)
+        best = np.fmax(best, tagged)
+    thr = np.maximum(np.abs(rf) * c1, floor)
+    accept = best >= thr
+    kk = (best.view(np.uint32) & np.uint32(15)).astype(np.int64)
+    target = ongrid_pointers(rho, dist_mat)                      # exact fallback everywhere ...
+    for k in range(13):                                          # ... overridden where accepted
+        sel = accept & (kk == k)
+        a = np.roll(rf, tuple(-x for x in offs[k]), axis=(0, 1, 2))
+        b = np.roll(rf, tuple(-x for x in offs[26 - k]), axis=(0, 1, 2))
+        la = np.roll(lin, tuple(-x for x in offs[k]), axis=(0, 1, 2))
+        lb = np.roll(lin, tuple(-x for x in offs[26 - k]), axis=(0, 1, 2))
+        target[sel] = np.where(a >= b, la, lb)[sel]
+    return target, accept
+
+
+@pytest.mark.parametrize('kind', ['smooth', 'noisy', 'quantised', 'tiny'])
+def test_seed_field_is_ascending_with_the_exact_maxima(kind):
+    """every seed pointer goes strictly uphill in the exact density (so the field is acyclic)
+    and the fixed points are exactly the ongrid maxima"""
+    from pybader_b200 import geometry as geo
+    from tests.shard_model import ongrid_pointers
+    rng = np.random.default_rng(len(kind))
+    shape = (14, 11, 17)
+    lattice = np.diag([3.0, 2.5, 4.0]) + rng.uniform(-0.3, 0.3, (3, 3))
+    f = np.stack(np.meshgrid(*[np.arange(n) / n for n in shape], indexing='ij'), -1)
+    rho = np.full(shape, 1e-3)
+    for _ in range(4):
+        c0, s, a = rng.random(3), rng.uniform(0.1, 0.3), rng.uniform(0.5, 2.0)
+        d = (f - c0 + 0.5) % 1.0 - 0.5
+        rho += a * np.exp(-(d ** 2).sum(-1) / (2 * s * s))
+    if kind == 'noisy':
+        rho *= 1.0 + 0.5 * rng.random(shape)
+    if kind == 'quantised':
+        rho = np.round(rho, 1) + 0.05
+    if kind == 'tiny':
+        rho *= 1e-44                                  # below fp32's normal range: all exact
+    dist = geo.distance_matrix(lattice, shape)
+    target, accept = seed_field_model(rho, dist)
+    exact = ongrid_pointers(rho, dist)
+    flat, lin = rho.reshape(-1), np.arange(rho.size)
+    moved = target.reshape(-1) != lin
+    assert np.all(flat[target.reshape(-1)[moved]] > flat[moved])
+    np.testing.assert_array_equal(~moved, exact.reshape(-1) == lin)      # same maxima
+    # where accepted, the chosen neighbour satisfies the reference's own criterion
+    sel = accept.reshape(-1)
+    assert np.all(sel <= moved)
+    if kind in ('smooth', 'noisy'):
+        assert sel.mean() > 0.9
+    if kind == 'tiny':
+        assert not sel.any()
