@@ -17,6 +17,10 @@
  *  - dist_mat is the reference's 3x3x3 table verbatim (interface.py:242-259;
  *    index 2 on an axis is the step -1), T_grad its 3x3 (interface.py:285-290).
  *  - one handle = one device = one stream; calls on a handle must not overlap.
+ *  - the file entry points at the end (bdr_parse_text, bdr_format_grid and their
+ *    helpers) stand in for the number blocks of the reference's readers and
+ *    writers (pybader/io/vasp.py, pybader/io/cube.py) and take no handle;
+ *    bdr_format_grid, bdr_parse_token_host and bdr_host_free need no device.
  */
 #ifndef BADER_B200_H
 #define BADER_B200_H
