@@ -132,7 +132,23 @@ def cpu_step(orc, rho, dist, T):
     return vol
 
 
-def cpu_baseline_leg(n=256):
+def cpu_baseline_leg(n=256, port=False):
+    """the reference beside the GPU number: the unmodified pybader (numba, all host
+    threads) on a bounded sample, else the single-threaded C port"""
+    if not port:
+        ref, why = load_numba_reference()
+        if ref is not None:
+            cores = os.cpu_count() or 1
+            sp = 96.0
+            rho, dist, T = ref_sample_inputs(sp)
+            t0 = time.perf_counter()
+            numba_step(ref, rho, dist, T, cores)
+            dt = time.perf_counter() - t0
+            return {"value": rho.size / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                    "sample": f"{rho.shape[0]}^3 periodic cell, 2x2x2 jittered atoms of the same workload "
+                              f"family ({sp:.0f}-voxel atom spacing), unmodified pybader thread handlers "
+                              f"bader_calc('neargrid') + refine(('changed', 2)), threads={cores}, JIT warm, "
+                              f"{dt:.1f} s"}
     from oracle import pyoracle as orc
     rho, dist, T = cpu_sample_inputs(n)
     cpu_step(orc, rho[:32, :32, :32].copy(), dist, T)          # load / warm the .so
@@ -145,38 +161,108 @@ def cpu_baseline_leg(n=256):
                       f"{dt:.1f} s on one host core"}
 
 
+def ref_sample_inputs(spacing, n_atoms_axis=2):
+    """bounded sample for the reference arm: a periodic cubic cell of 2x2x2 jittered atoms of
+    the bench workload family (same voxel size, same Gaussian widths relative to the atom
+    spacing, every atom with six neighbours like in the 5x5x5 / 10x10x10 cells of the GPU
+    arm), `spacing` voxels between atoms"""
+    from pybader_b200 import geometry as geo, synth
+    n = int(round(n_atoms_axis * spacing))
+    c = synth.case_lattice_sites((n, n, n), (n_atoms_axis,) * 3, (n * VOXEL,) * 3, seed=2048)
+    tx, ty, tz = synth.separable_tables(c)
+    rho = np.ascontiguousarray(np.einsum('ai,aj,ak->ijk', tx, ty, tz, optimize=True))
+    return rho, geo.distance_matrix(c['lattice'], rho.shape), geo.T_grad(c['lattice'], rho.shape)
+
+
+def numba_step(ref, rho, dist, T, threads):
+    """the reference's own hot path, unmodified: thread_handlers.bader_calc('neargrid') +
+    thread_handlers.refine('neargrid', ('changed', 2)) (thread_handlers.py:15-75, 128-236)"""
+    from baseline.refload import quiet
+    vol = np.zeros(rho.shape, dtype=ref['utils'].dtype_calc(-rho.size))
+    with quiet():
+        mx, vol = ref['th'].bader_calc('neargrid', rho, vol, dist, T, threads)
+        ref['th'].refine('neargrid', ('changed', 2), rho, vol, dist, T, threads)
+    return vol
+
+
+def load_numba_reference():
+    """(ref modules, None) or (None, why not)"""
+    try:
+        from baseline.refload import import_reference
+        ref = import_reference()
+        # JIT warm-up of every signature the step uses, on a 16^3 cell
+        rho, dist, T = ref_sample_inputs(8)
+        numba_step(ref, rho, dist, T, 1)
+        numba_step(ref, rho, dist, T, 2)
+        return ref, None
+    except Exception as e:                      # numba / pybader missing on this box
+        return None, f"{type(e).__name__}: {e}"
+
+
+def pick_spacing(rate, steps, budget_s):
+    """largest atom spacing (voxels) <= the GPU arm's whose 2x2x2-atom cell lets `steps`
+    steps fit the time budget at `rate` voxels/s"""
+    for sp in (SPACING, 176.0, 160.0, 144.0, 128.0, 112.0, 96.0, 80.0, 64.0):
+        if steps * (2 * sp) ** 3 / rate <= budget_s:
+            return sp
+    return 48.0
+
+
 def reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (the C oracle port; the
-    reference itself is numba and cannot travel) on all host cores: one
-    independent brick per thread, like the reference's brick threading at its
-    ideal efficiency."""
+    """--impl reference: the UNMODIFIED reference (pybader's numba thread handlers from
+    baseline/_ref) on all host cores, on a bounded sample of the GPU arm's workload family.
+    If pybader / numba cannot be imported on this box the C port of the same algorithm
+    (oracle/) runs instead, one independent cell per host thread, and the line says so."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from oracle import pyoracle as orc
-    n = args.ref_sample
     cores = os.cpu_count() or 1
-    rho, dist, T = cpu_sample_inputs(n)
-    bricks = [rho.copy() for _ in range(cores)]
-    cpu_step(orc, rho[:32, :32, :32].copy(), dist, T)
+    shape = SHAPES.get(args.gpus, SHAPES[1])
+    ref, why = (None, 'disabled by --ref-port') if args.ref_port else load_numba_reference()
+    total_steps = args.steps + args.warmup
+    if ref is not None:
+        kind = 'reference'
+        rho, dist, T = ref_sample_inputs(48)
+        t0 = time.perf_counter()
+        numba_step(ref, rho, dist, T, cores)
+        rate = rho.size / (time.perf_counter() - t0)
+        sp = args.ref_spacing or pick_spacing(rate * 1.5, total_steps, args.ref_budget)
+        rho, dist, T = ref_sample_inputs(sp)
+        n_vox = rho.size
 
-    def one_step():
-        ths = [threading.Thread(target=cpu_step, args=(orc, b, dist, T)) for b in bricks]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
+        def one_step():
+            numba_step(ref, rho, dist, T, cores)
 
-    for _ in range(min(args.warmup, 1)):
+        sample = (f"one {rho.shape[0]}^3 periodic cell per step: 2x2x2 jittered atoms of the same "
+                  f"workload family ({sp:.1f}-voxel atom spacing; the GPU arm's is {SPACING}), "
+                  f"unmodified pybader {ref['root']} thread_handlers.bader_calc('neargrid') + "
+                  f"refine('neargrid', ('changed', 2)), threads={cores}, numba JIT warmed on 16^3")
+    else:
+        kind = 'port'
+        from oracle import pyoracle as orc
+        n = args.ref_sample
+        rho, dist, T = cpu_sample_inputs(n)
+        bricks = [rho.copy() for _ in range(cores)]
+        cpu_step(orc, rho[:32, :32, :32].copy(), dist, T)
+        n_vox = cores * rho.size
+
+        def one_step():
+            ths = [threading.Thread(target=cpu_step, args=(orc, b, dist, T)) for b in bricks]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+
+        sample = (f"pybader not importable here ({why}); C port instead: {cores} independent {n}^3 "
+                  f"cells per step (one host thread each), same workload family; oracle/ port of "
+                  f"methods.neargrid + thread_handlers.refine('changed',2)")
+    for _ in range(args.warmup):
         one_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         one_step()
     dt = (time.perf_counter() - t0) / args.steps
-    value = cores * rho.size / dt
-    shape = SHAPES.get(args.gpus, SHAPES[1])
-    sample = (f"{cores} independent {n}^3 bricks per step (one host thread each), same workload "
-              f"family; oracle C port of methods.neargrid + thread_handlers.refine('changed',2)")
+    value = n_vox / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -184,7 +270,7 @@ def reference_arm(args):
         "data": "synthetic",
         "config": {"workload": workload_name(shape), "method": "neargrid",
                    "refine_method": "neargrid", "refine_mode": ["changed", 2]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -281,7 +367,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=0, help='override: cubic N^3 single-GPU grid')
     ap.add_argument('--cpu-sample', type=int, default=256)
-    ap.add_argument('--ref-sample', type=int, default=160)
+    ap.add_argument('--ref-sample', type=int, default=160, help='port fallback: cell edge')
+    ap.add_argument('--ref-spacing', type=float, default=0.0,
+                    help='reference arm: atom spacing in voxels of its 2x2x2-atom cell (0: picked to fit --ref-budget)')
+    ap.add_argument('--ref-budget', type=float, default=200.0, help='reference arm: seconds for all steps')
+    ap.add_argument('--ref-port', action='store_true', help='reference arm / cpu baseline: force the C port')
     ap.add_argument('--halo', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -376,7 +466,7 @@ def main():
         del host_rho, host_lab
 
     clock_info = clocks.stop()      # sampled through both timed regions (device steps and e2e)
-    cpu = None if args.no_cpu else cpu_baseline_leg(args.cpu_sample)
+    cpu = None if args.no_cpu else cpu_baseline_leg(args.cpu_sample, args.ref_port)
     e.close()
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,

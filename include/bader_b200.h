@@ -75,6 +75,10 @@ int bdr_upload_density(bdr_ctx *ctx, int which, const double *host);
 int bdr_download_density(bdr_ctx *ctx, int which, double *host);
 /* Make slot `which` an alias of slot `of` (e.g. density is reference).      */
 int bdr_alias_density(bdr_ctx *ctx, int which, int of);
+/* Device-to-device copy of slot `src` into slot `dst` (Bader.reference = another
+ * density that is already resident, interface.py:136-137 and the -ref flow of
+ * entry_points.py:184-194).                                                  */
+int bdr_copy_density(bdr_ctx *ctx, int dst, int src);
 /* Labels in/out in any of the reference's label dtypes (jits.py:9: int8/16/
  * 32/64); elem_size in bytes.  Narrowing happens on the device
  * (utils.dtype_change, utils.py:256-259).                                   */
@@ -89,6 +93,9 @@ int bdr_clear_labels(bdr_ctx *ctx, int which);
  * charge = (sum density)*voxel_volume and volume = count*voxel_volume.      */
 int bdr_vacuum_assign(bdr_ctx *ctx, double vac_tol, double voxel_volume,
                       int which_density, double *vac_charge, double *vac_volume);
+/* number of voxels the last bdr_vacuum_assign on this handle labelled -1 (0: the
+ * host copy of the labels is still current and needs no download)             */
+int bdr_vacuum_count(bdr_ctx *ctx, int64_t *count);
 
 /* thread_handlers.bader_calc (thread_handlers.py:15-75) -> methods.ongrid /
  * methods.neargrid (methods.py:15-219, 222-611).  Consumes the BADER labels
@@ -254,6 +261,13 @@ int bdr_parse_release(int device);
  * pageable arrays cross PCIe at a fifth of the rate); NULL on failure         */
 void *bdr_host_alloc(int64_t bytes);
 int bdr_host_free(void *ptr);
+/* 64-bit content hash of a host buffer on `threads` host threads (<= 0: all), and
+ * whether every byte is zero.  The reference passes numpy arrays between its stages
+ * (interface.py:449-534) and always reads the array it is given; the Python session
+ * keeps device copies and keys them on this hash of the WHOLE array, so an in-place
+ * edit between stages re-uploads instead of computing on stale device data.  No
+ * device needed.                                                               */
+int bdr_host_hash(const void *data, int64_t nbytes, int threads, uint64_t *hash, int *all_zero);
 /* the same conversion for one token on the CPU (tests; no device needed):
  * 0 converted, 2 not handled exactly (ask strtod)                             */
 int bdr_parse_token_host(const char *token, int64_t len, double *out);

@@ -26,11 +26,13 @@ SIGNATURES = {
     "bdr_upload_density": ([_p, _int, _p], _int),
     "bdr_download_density": ([_p, _int, _p], _int),
     "bdr_alias_density": ([_p, _int, _int], _int),
+    "bdr_copy_density": ([_p, _int, _int], _int),
     "bdr_upload_labels": ([_p, _int, _p, _int], _int),
     "bdr_download_labels": ([_p, _int, _p, _int], _int),
     "bdr_download_known": ([_p, _p], _int),
     "bdr_clear_labels": ([_p, _int], _int),
     "bdr_vacuum_assign": ([_p, _f64, _f64, _int, ctypes.POINTER(_f64), ctypes.POINTER(_f64)], _int),
+    "bdr_vacuum_count": ([_p, ctypes.POINTER(_i64)], _int),
     "bdr_bader_calc": ([_p, _int, _p, _p, ctypes.POINTER(_i64)], _int),
     "bdr_get_maxima": ([_p, _p, _i64], _int),
     "bdr_refine": ([_p, _int, _int, _i64, _p, _p, ctypes.POINTER(_i64), _p, _i64], _int),
@@ -72,6 +74,7 @@ SIGNATURES = {
     "bdr_format_grid": ([ctypes.c_char_p, _p, _i64, _i64, _i64, _int, _i64, _int, _int, _int], _int),
     "bdr_host_alloc": ([_i64], _p),
     "bdr_host_free": ([_p], _int),
+    "bdr_host_hash": ([_p, _i64, _int, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(_int)], _int),
 }
 
 _lib = None

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <mutex>
+#include <thread>
 
 namespace bdr {
 thread_local std::string g_err;
@@ -857,17 +858,24 @@ static int charge_sum_dev(bdr_ctx *c, int which_labels, int which_density, doubl
     const unsigned nb = blocks_for(n_own, (int)per_block);
     const int32_t *lab = c->labels[which_labels] + c->own_lo;
     dens += c->own_lo;
+    TRY(zero_counter(c, CNT_ERROR));
     if (n <= SUM_BINS)
         LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<true>, nb, 256, 0, dens, lab, n_own, (int)n, q, cnt,
-               per_block);
+               per_block, c->d_cnt + CNT_ERROR);
     else
         LAUNCH(c, BDR_K_CHARGE_SUM, k_charge_sum<false>, nb, 256, 0, dens, lab, n_own, (int)n, q, cnt,
-               per_block);
+               per_block, c->d_cnt + CNT_ERROR);
     std::vector<double> hq((size_t)n);
     std::vector<unsigned long long> hc((size_t)n);
     CU(cudaMemcpyAsync(hq.data(), q, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(hc.data(), cnt, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    TRY(read_counters(c));
+    if (c->h_cnt[CNT_ERROR]) {
+        const unsigned long long bad = c->h_cnt[CNT_ERROR];
+        TRY(zero_counter(c, CNT_ERROR));
+        return fail_msg("charge_sum: " + std::to_string(bad) + " voxels carry a label >= " + std::to_string(n) +
+                        " (the charge / volume arrays have " + std::to_string(n) + " entries)");
+    }
     for (int64_t i = 0; i < n; ++i) {
         // the reference adds into caller-provided (zeroed) arrays, then scales
         if (charge) charge[i] = (charge[i] + hq[(size_t)i]) * dV;
@@ -1202,6 +1210,19 @@ int bdr_alias_density(bdr_ctx *c, int which, int of) {
     return 0;
 }
 
+int bdr_copy_density(bdr_ctx *c, int dst, int src) {
+    TRY(check(c));
+    if (dst < 0 || dst > 2 || src < 0 || src > 2) return fail_msg("bdr_copy_density: bad argument");
+    const double *from = rho_ptr(c, src);
+    if (!from) return fail_msg("bdr_copy_density: source slot is empty");
+    if (c->rho[dst] == from) return 0;
+    // (a dst that merely aliased src gets storage of its own here)
+    TRY(ensure_rho(c, dst));
+    CU(cudaMemcpyAsync(c->rho[dst], from, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int bdr_clear_labels(bdr_ctx *c, int which) {
     TRY(check(c));
     if (which < 0 || which > 1) return fail_msg("bdr_clear_labels: bad argument");
@@ -1276,6 +1297,14 @@ int bdr_vacuum_assign(bdr_ctx *c, double vac_tol, double voxel_volume, int which
     c->vac_tol = vac_tol;
     if (vac_charge) *vac_charge = s * voxel_volume;
     if (vac_volume) *vac_volume = (double)c->h_cnt[CNT_VACUUM] * voxel_volume;
+    c->vac_count = (int64_t)c->h_cnt[CNT_VACUUM];
+    return 0;
+}
+
+int bdr_vacuum_count(bdr_ctx *c, int64_t *count) {
+    TRY(check(c));
+    if (!count) return fail_msg("bdr_vacuum_count: null out");
+    *count = c->vac_count;
     return 0;
 }
 
@@ -1430,6 +1459,8 @@ int bdr_surface_distance(bdr_ctx *c, int which, const double *lattice, const dou
 int bdr_volume_mask(bdr_ctx *c, int which_labels, int which_density, int64_t vol_num,
                     double *host_out) {
     TRY(check(c));
+    if (which_labels < 0 || which_labels > 1 || which_density < 0 || which_density > 2 || !host_out)
+        return fail_msg("bdr_volume_mask: bad argument");
     if (!c->labels[which_labels]) return fail_msg("bdr_volume_mask: label set is empty");
     const double *dens = rho_ptr(c, which_density);
     if (!dens) return fail_msg("bdr_volume_mask: density slot is empty");
@@ -1467,6 +1498,8 @@ int bdr_run(bdr_ctx *c, const double *host_density, double vac_tol, double voxel
     }
     const double t2 = now();
     if (n_maxima) *n_maxima = n;
+    if ((maxima || charge || volume) && n > max_cap)
+        return fail_msg("bdr_run: " + std::to_string(n) + " maxima do not fit max_cap = " + std::to_string(max_cap));
     if (maxima) TRY(bdr_get_maxima(c, maxima, max_cap));
     if (charge || volume) {
         for (int64_t i = 0; i < n; ++i) {
@@ -1525,6 +1558,67 @@ void *bdr_host_alloc(int64_t bytes) {
 }
 int bdr_host_free(void *p) {
     if (p) CU(cudaFreeHost(p));
+    return 0;
+}
+
+// Content fingerprint of a host array (the Python session keys device residency on
+// it: an in-place edit anywhere in the array must change the key).  All host threads
+// stream the bytes once; 64-bit words go through four independent multiply-xorshift
+// lanes per 4 KiB block, block hashes are combined with their position.  Also
+// reports whether every byte is zero (a fresh label array needs no upload).
+static inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+int bdr_host_hash(const void *data, int64_t nbytes, int threads, uint64_t *hash, int *all_zero) {
+    if ((!data && nbytes > 0) || nbytes < 0 || !hash) return fail_msg("bdr_host_hash: bad argument");
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    constexpr int64_t BLOCK = 1 << 16;
+    const int64_t nblocks = (nbytes + BLOCK - 1) / BLOCK;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nt, 64), (nblocks + 63) / 64));
+    std::vector<uint64_t> acc((size_t)nt, 0), orr((size_t)nt, 0);
+    auto work = [&](int t) {
+        uint64_t a = 0, nz = 0;
+        for (int64_t b = t; b < nblocks; b += nt) {
+            const int64_t lo = b * BLOCK, hi = std::min(nbytes, lo + BLOCK);
+            uint64_t h0 = 0x9E3779B97F4A7C15ULL, h1 = 0xC2B2AE3D27D4EB4FULL, h2 = 0x165667B19E3779F9ULL,
+                     h3 = 0x27D4EB2F165667C5ULL, o = 0;
+            int64_t i = lo;
+            for (; i + 32 <= hi; i += 32) {
+                uint64_t w[4];
+                memcpy(w, p + i, 32);
+                o |= w[0] | w[1] | w[2] | w[3];
+                h0 = (h0 ^ w[0]) * 0xFF51AFD7ED558CCDULL; h0 ^= h0 >> 29;
+                h1 = (h1 ^ w[1]) * 0xC4CEB9FE1A85EC53ULL; h1 ^= h1 >> 31;
+                h2 = (h2 ^ w[2]) * 0x9FB21C651E98DF25ULL; h2 ^= h2 >> 28;
+                h3 = (h3 ^ w[3]) * 0xD6E8FEB86659FD93ULL; h3 ^= h3 >> 32;
+            }
+            for (; i < hi; ++i) {
+                o |= p[i];
+                h0 = (h0 ^ p[i]) * 0xFF51AFD7ED558CCDULL; h0 ^= h0 >> 29;
+            }
+            nz |= o;
+            a += mix64(mix64(h0) + 3 * mix64(h1) + 5 * mix64(h2) + 7 * mix64(h3) + (uint64_t)b * 0x9E3779B97F4A7C15ULL);
+        }
+        acc[(size_t)t] = a;
+        orr[(size_t)t] = nz;
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    uint64_t h = mix64((uint64_t)nbytes), nz = 0;
+    for (int t = 0; t < nt; ++t) {
+        h += acc[(size_t)t];   // block hashes carry their position: the sum is order-free
+        nz |= orr[(size_t)t];
+    }
+    *hash = mix64(h);
+    if (all_zero) *all_zero = nz == 0;
     return 0;
 }
 

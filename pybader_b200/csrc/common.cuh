@@ -99,6 +99,7 @@ struct bdr_ctx {
     int32_t *labels[2] = {nullptr, nullptr};
     int vac_mode = 0;      // how the stencil pass learns the vacuum mask (VAC_* in kernels.cuh)
     double vac_tol = 0.0;
+    int64_t vac_count = 0;  // voxels the last bdr_vacuum_assign marked
     bool verify_fixed_point = false;  // BDR_OPT_VERIFY_FIXED_POINT
     int8_t *known = nullptr;
     uint32_t *ebits = nullptr;  // edge pass: 1 bit per voxel, nzw words per (x,y) row

@@ -68,6 +68,9 @@ class Engine:
     def alias_density(self, which, of):
         check(self.lib.bdr_alias_density(self.h, which, of))
 
+    def copy_density(self, dst, src):
+        check(self.lib.bdr_copy_density(self.h, dst, src))
+
     def upload_labels(self, which, labels):
         labels = np.ascontiguousarray(labels)
         if labels.shape != self.shape:
@@ -95,11 +98,15 @@ class Engine:
         check(self.lib.bdr_clear_labels(self.h, which))
 
     # -- hot path ------------------------------------------------------------
-    def vacuum_assign(self, vac_tol, voxel_volume, which_density=RHO_REFERENCE):
+    def vacuum_assign(self, vac_tol, voxel_volume, which_density=RHO_REFERENCE, want_count=False):
         q, v = ctypes.c_double(0), ctypes.c_double(0)
         check(self.lib.bdr_vacuum_assign(self.h, float(vac_tol), float(voxel_volume),
                                          which_density, ctypes.byref(q), ctypes.byref(v)))
-        return q.value, v.value
+        if not want_count:
+            return q.value, v.value
+        n = ctypes.c_int64(0)
+        check(self.lib.bdr_vacuum_count(self.h, ctypes.byref(n)))
+        return q.value, v.value, n.value
 
     def bader_calc(self, method, dist_mat, T_grad):
         d, t = _f64(dist_mat), _f64(T_grad)

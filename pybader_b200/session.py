@@ -1,15 +1,23 @@
 """Device residency for the reference-shaped entry points.
 
-The reference passes numpy arrays between stages (interface.py:449-534).  To
-keep those signatures while not re-uploading a density for every stage, one
-`Session` per grid shape remembers which host arrays its device buffers mirror.
-An array is recognised by its address, shape, dtype and a strided sample of its
-bytes; a mismatch simply re-uploads.
+The reference passes numpy arrays between stages (interface.py:449-534) and
+every stage reads the array it is given.  To keep those signatures without
+re-uploading a density for every stage, one `Session` per grid shape remembers
+which host arrays its device buffers mirror.
+
+The rule that makes a stale hit impossible: an array is recognised by its
+shape, dtype and a 64-bit hash of ALL of its bytes (`bdr_host_hash`, every
+host thread streams the array once -- a fraction of what the upload it saves
+costs).  An in-place edit anywhere in the array, or a different array at a
+recycled address, changes the key and the array is uploaded again.  The
+reference density is only ever read from slot RHO_REFERENCE: a density that
+is resident in another slot is copied there on the device, never assumed.
 """
-import zlib
+import ctypes
 
 import numpy as np
 
+from . import _lib
 from .engine import (LABELS_ATOMS, LABELS_BADER, RHO_CHARGE, RHO_REFERENCE, RHO_SPIN, Engine)
 
 _sessions = {}
@@ -22,13 +30,20 @@ def set_device(device):
     _device = int(device)
 
 
+def content_hash(a):
+    """(64-bit hash of every byte, all bytes zero?) of a C-contiguous view of `a`."""
+    a = np.ascontiguousarray(a)
+    h, z = ctypes.c_uint64(0), ctypes.c_int(0)
+    _lib.check(_lib.load().bdr_host_hash(a.ctypes.data_as(ctypes.c_void_p), a.nbytes, 0,
+                                         ctypes.byref(h), ctypes.byref(z)))
+    return h.value, bool(z.value)
+
+
 def fingerprint(a):
+    """Residency key of a host array: shape, dtype and the hash of its whole content
+    (the address is deliberately not part of it: equal content is equal data)."""
     a = np.asarray(a)
-    flat = a.reshape(-1)
-    step = max(1, flat.size // 4096)
-    sample = np.ascontiguousarray(flat[::step])
-    return (a.__array_interface__['data'][0], a.shape, a.dtype.str, a.strides,
-            zlib.crc32(sample.tobytes()))
+    return (a.shape, a.dtype.str, content_hash(a)[0])
 
 
 class Session:
@@ -37,35 +52,65 @@ class Session:
         self.shape = tuple(shape)
         self.rho_key = [None, None, None]
         self.label_key = [None, None]
+        self.uploads = {'density': 0, 'labels': 0}   # host -> device copies made (tests, bench)
 
     # densities -------------------------------------------------------------
+    def _upload_density(self, slot, arr, key):
+        self.engine.upload_density(slot, arr)
+        self.rho_key[slot] = key
+        self.uploads['density'] += 1
+
     def density_slot(self, arr, prefer=RHO_CHARGE):
         """Slot holding `arr`, uploading into `prefer` if it is not resident."""
         key = fingerprint(arr)
         for slot in (RHO_REFERENCE, RHO_CHARGE, RHO_SPIN):
             if self.rho_key[slot] == key:
                 return slot
-        self.engine.upload_density(prefer, arr)
-        self.rho_key[prefer] = key
-        if prefer == RHO_REFERENCE:
-            # stale aliases must not survive a new reference
-            for slot in (RHO_CHARGE, RHO_SPIN):
-                if self.rho_key[slot] is None:
-                    self.engine.alias_density(slot, RHO_REFERENCE)
+        self._upload_density(prefer, arr, key)
         return prefer
 
     def reference(self, arr):
-        return self.density_slot(arr, prefer=RHO_REFERENCE)
+        """Make `arr` the reference density (slot RHO_REFERENCE, the only slot the
+        maximum search, the refinement, the vacuum mask and the surface distance
+        read): a hit in another slot is copied over on the device, anything else
+        is uploaded."""
+        key = fingerprint(arr)
+        if self.rho_key[RHO_REFERENCE] == key:
+            return RHO_REFERENCE
+        for slot in (RHO_CHARGE, RHO_SPIN):
+            if self.rho_key[slot] == key:
+                self.engine.copy_density(RHO_REFERENCE, slot)
+                self.rho_key[RHO_REFERENCE] = key
+                return RHO_REFERENCE
+        self._upload_density(RHO_REFERENCE, arr, key)
+        return RHO_REFERENCE
+
+    def free_density_slot(self):
+        """First slot that mirrors no host array: reference, then charge, then spin."""
+        for slot in (RHO_REFERENCE, RHO_CHARGE, RHO_SPIN):
+            if self.rho_key[slot] is None:
+                return slot
+        return RHO_SPIN
 
     # labels ----------------------------------------------------------------
-    def label_slot(self, arr, prefer=LABELS_BADER):
-        key = fingerprint(arr)
-        for slot in (LABELS_BADER, LABELS_ATOMS):
+    def label_slot(self, arr, prefer=LABELS_BADER, force=None):
+        """Slot holding the labels `arr`; uploads into `prefer` if they are not
+        resident.  With `force` the labels must end up in that slot."""
+        arr = np.asarray(arr)
+        digest, all_zero = content_hash(arr)
+        key = (arr.shape, arr.dtype.str, digest)
+        order = (LABELS_BADER, LABELS_ATOMS) if force is None else (force,)
+        for slot in order:
             if self.label_key[slot] == key:
                 return slot
-        self.engine.upload_labels(prefer, arr)
-        self.label_key[prefer] = key
-        return prefer
+        slot = prefer if force is None else force
+        if all_zero:
+            self.engine.clear_labels(slot)   # fresh labels (interface.py:456-457): nothing to copy
+        else:
+            self.engine.upload_labels(slot, arr)
+            self.uploads['labels'] += 1
+        self.label_key[slot] = key
+        return slot
 
     def labels_to_host(self, slot, dtype=None, out=None):
         if out is not None:

@@ -22,9 +22,7 @@ def bader_calc(method, density, volumes, dist_mat, T_grad, threads=1):
         raise AttributeError(f"module 'pybader.methods' has no attribute '{method}'")
     s = session.get(density.shape)
     s.reference(density)
-    slot = s.label_slot(volumes, prefer=LABELS_BADER)
-    if slot != LABELS_BADER:
-        s.engine.upload_labels(LABELS_BADER, volumes)
+    s.label_slot(volumes, force=LABELS_BADER)
     bader_max = s.engine.bader_calc(method, dist_mat, T_grad)
     out = s.labels_to_host(LABELS_BADER, dtype_calc(-bader_max.shape[0]))
     return bader_max, out
@@ -51,10 +49,7 @@ refine.last_history = []
 
 def assign_to_atoms(bader_max, atoms, lattice, volumes, threads=1):
     s = session.get(volumes.shape)
-    slot = s.label_slot(volumes, prefer=LABELS_BADER)
-    if slot != LABELS_BADER:
-        s.engine.upload_labels(LABELS_BADER, volumes)
-        s.label_key[LABELS_BADER] = session.fingerprint(volumes)
+    s.label_slot(volumes, force=LABELS_BADER)
     bader_atoms, bader_distance = s.engine.assign_atoms(bader_max, atoms, lattice)
     atoms_volumes = s.labels_to_host(LABELS_ATOMS, dtype_calc(-np.asarray(atoms).shape[0]))
     return bader_atoms, bader_distance, atoms_volumes

@@ -10,7 +10,7 @@
 import numpy as np
 
 from . import session
-from .engine import LABELS_BADER, RHO_CHARGE, RHO_REFERENCE, RHO_SPIN, Engine
+from .engine import LABELS_BADER, RHO_CHARGE, Engine
 
 
 def dtype_calc(max_val):
@@ -33,12 +33,13 @@ def vacuum_assign(reference, volumes, vac_tol, density, voxel_volume):
     s = session.get(reference.shape)
     s.reference(reference)
     dslot = s.density_slot(density, prefer=RHO_CHARGE)
-    if volumes.any():
-        s.engine.upload_labels(LABELS_BADER, volumes)
-    else:
-        s.engine.clear_labels(LABELS_BADER)
-    charge, volume = s.engine.vacuum_assign(vac_tol, voxel_volume, dslot)
-    s.labels_to_host(LABELS_BADER, out=volumes)
+    # fresh (all-zero) labels are cleared on the device, labelled ones (bader-read's
+    # re-threshold flow, entry_points.py:238-255) uploaded; the content hash that keys
+    # residency tells which, so the host array is read once
+    s.label_slot(volumes, force=LABELS_BADER)
+    charge, volume, count = s.engine.vacuum_assign(vac_tol, voxel_volume, dslot, want_count=True)
+    if count:
+        s.labels_to_host(LABELS_BADER, out=volumes)   # only then did any label change
     return volumes, charge, volume
 
 
@@ -47,13 +48,7 @@ def charge_sum(charge, volume, voxel_volume, density, volumes):
     lslot = s.label_slot(volumes, prefer=LABELS_BADER)
     # first free slot: reference, then charge, then spin (so charge and spin
     # both stay resident next to the reference)
-    if s.rho_key[RHO_REFERENCE] is None:
-        prefer = RHO_REFERENCE
-    elif s.rho_key[RHO_CHARGE] is None:
-        prefer = RHO_CHARGE
-    else:
-        prefer = RHO_SPIN
-    dslot = s.density_slot(density, prefer=prefer)
+    dslot = s.density_slot(density, prefer=s.free_density_slot())
     s.engine.charge_sum(lslot, dslot, voxel_volume, charge, volume)
 
 
@@ -69,6 +64,5 @@ def atom_assign(bader_max, atoms, lattice, i_c=None):
 def volume_mask(volumes, density, vol_num):
     s = session.get(volumes.shape)
     lslot = s.label_slot(volumes, prefer=LABELS_BADER)
-    dslot = s.density_slot(density, prefer=RHO_CHARGE if s.rho_key[RHO_REFERENCE] is not None
-                           else RHO_REFERENCE)
+    dslot = s.density_slot(density, prefer=s.free_density_slot())
     return s.engine.volume_mask(lslot, dslot, vol_num)

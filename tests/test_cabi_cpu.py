@@ -92,10 +92,42 @@ def test_geometry_matches_reference_formulas():
 
 
 def test_session_fingerprint_detects_change():
-    from pybader_b200.session import fingerprint
+    """residency keys hash the WHOLE array: an edit of any single element changes the
+    key (the old strided sample missed most voxels); equal content is
+    equal data, whatever buffer holds it"""
+    from pybader_b200.session import content_hash, fingerprint
     a = np.zeros((8, 8, 8))
     k = fingerprint(a)
     assert fingerprint(a) == k
-    a[0, 0, 0] = 1
-    assert fingerprint(a) != k
-    assert fingerprint(a.copy()) != fingerprint(a)   # another buffer
+    assert content_hash(a)[1] is True
+    for idx in np.ndindex(a.shape):
+        a[idx] = 1e-300
+        assert fingerprint(a) != k, idx
+        assert content_hash(a)[1] is False
+        a[idx] = 0
+    assert fingerprint(a.copy()) == fingerprint(a)
+    assert fingerprint(a.astype(np.float32)) != fingerprint(a)
+    rng = np.random.default_rng(5)
+    b = rng.integers(-1, 100, size=(37, 41, 43)).astype(np.int16)   # ragged: tail bytes, several blocks
+    kb = fingerprint(b)
+    flat = b.reshape(-1)
+    for pos in list(rng.integers(0, flat.size, 200)) + [0, flat.size - 1]:
+        old = flat[pos]
+        flat[pos] = old + 1
+        assert fingerprint(b) != kb, pos
+        flat[pos] = old
+    assert fingerprint(b) == kb
+    # swapping two blocks of the buffer is a different array
+    c = np.arange(1 << 16, dtype=np.int64)
+    d = np.concatenate([c[1 << 15:], c[:1 << 15]])
+    assert fingerprint(c) != fingerprint(d)
+    # independent of the thread count
+    import ctypes
+    from pybader_b200 import _lib
+    big = rng.random(3_000_000)
+    hs = []
+    for nt in (1, 2, 7):
+        h, z = ctypes.c_uint64(0), ctypes.c_int(0)
+        assert _lib.load().bdr_host_hash(big.ctypes.data, big.nbytes, nt, ctypes.byref(h), ctypes.byref(z)) == 0
+        hs.append(h.value)
+    assert len(set(hs)) == 1

@@ -1,0 +1,260 @@
+"""The drop-in boundary, end to end: `pybader_b200.install()` rebinds the names
+`pybader/interface.py:16-18` imported, then the UNMODIFIED reference `Bader` object
+(from baseline/_ref, else /root/reference) runs `Bader.__call__` (interface.py:399-447)
+on the CUDA engine.  Results are compared with golden outputs of the very same call made
+with the reference's own numba hot path (tests/golden_call/make_call_golden.py).
+
+Also here: the residency rules of pybader_b200.session (ADVICE r1 / VERDICT r1 #9) --
+a reference that alternates between two arrays, and a user edit of `bader_volumes`
+between stages -- checked against results computed from scratch.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden_call')
+
+pytestmark = pytest.mark.gpu
+
+
+def load(name):
+    path = os.path.join(GOLD, name + '.npz')
+    if not os.path.exists(path):
+        pytest.skip(f"{name}.npz not generated")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+def density_from_tables(tx, ty, tz):
+    rho = np.zeros((tx.shape[1], ty.shape[1], tz.shape[1]))
+    for a in range(tx.shape[0]):
+        rho += (tx[a][:, None, None] * ty[a][None, :, None]) * tz[a][None, None, :]
+    return rho
+
+
+@pytest.fixture(scope='module')
+def ref():
+    from baseline.refload import import_reference
+    try:
+        return import_reference()
+    except ImportError as e:           # numba or the reference install missing on this box
+        pytest.skip(f"reference not importable: {e}")
+
+
+@pytest.fixture()
+def installed(ref):
+    import pybader_b200
+    from pybader_b200 import session, thread_handlers as th, utils as ut
+    old = pybader_b200.install(ref['interface'], readers=False)
+    itf = ref['interface']
+    assert itf.bader_calc is th.bader_calc and itf.refine is th.refine
+    assert itf.assign_to_atoms is th.assign_to_atoms and itf.surface_distance is th.surface_distance
+    assert itf.charge_sum is ut.charge_sum and itf.vacuum_assign is ut.vacuum_assign
+    yield ref
+    pybader_b200.uninstall(old, ref['interface'])
+    assert itf.bader_calc is ref['th'].bader_calc
+    session.close_all()
+
+
+def make_bader(ref, density, g, profile='DEFAULT', reference=None, **config):
+    from baseline.refload import quiet
+    info = dict(filename='golden', prefix='', file_type='synthetic',
+                voxel_offset=np.asarray(g['voxel_offset'], dtype=np.float64), out_dest=os.devnull)
+    b = ref['Bader'](density, np.asarray(g['lattice'], dtype=np.float64),
+                     np.ascontiguousarray(g['atoms'], dtype=np.float64), info)
+    if profile != 'DEFAULT':
+        b.load_config(profile)
+    b.apply_config(dict(threads=1, **config))
+    if reference is not None:
+        b.reference = reference
+    with quiet():
+        b()
+    return b
+
+
+def compare(b, g, labels_exact, min_agree=0.999):
+    # geometry the unmodified Bader derived and handed to the engine (a1)
+    np.testing.assert_array_equal(b.distance_matrix, g['distance_matrix'])
+    np.testing.assert_array_equal(b.T_grad, g['T_grad'])
+    # maxima: same voxels in the same order
+    np.testing.assert_array_equal(b.bader_maxima_fractional, g['bader_maxima_fractional'])
+    np.testing.assert_array_equal(b.bader_atoms, g['bader_atoms'])
+    np.testing.assert_allclose(b.bader_distance, g['bader_distance'], rtol=1e-12, atol=1e-14)
+    assert b.atoms_volumes.dtype == g['atoms_volumes'].dtype
+    for key in ('atoms_volumes', 'bader_volumes'):
+        if key not in g:
+            continue
+        mine, theirs = getattr(b, key), g[key]
+        assert mine.dtype == theirs.dtype and mine.shape == theirs.shape
+        differ = int(np.count_nonzero(mine != theirs))
+        if labels_exact:
+            assert differ == 0, (key, differ)
+        else:
+            assert differ <= (1 - min_agree) * mine.size, (key, differ)
+    for key in ('bader_charge', 'bader_volume', 'bader_spin', 'atoms_charge', 'atoms_volume',
+                'atoms_spin'):
+        if key in g:
+            np.testing.assert_allclose(getattr(b, key), g[key], rtol=1e-6, atol=1e-12, err_msg=key)
+    np.testing.assert_allclose(b.atoms_surface_distance, g['atoms_surface_distance'], rtol=1e-9)
+    assert b.vacuum_charge == pytest.approx(float(g['vacuum_charge']), rel=1e-12, abs=1e-300)
+    assert b.vacuum_volume == pytest.approx(float(g['vacuum_volume']), rel=1e-12, abs=1e-300)
+
+
+def test_bader_call_default_profile_c1(installed):
+    """BASELINE config 1 through Bader.__call__, DEFAULT profile (neargrid + refine
+    ('changed', 2) on bader_volumes, sums, atoms, surface distance)"""
+    g = load('c1_default')
+    rho = density_from_tables(g['tx'], g['ty'], g['tz'])
+    b = make_bader(installed, {'charge': rho}, g)
+    compare(b, g, labels_exact=False)
+    differ = int(np.count_nonzero(b.bader_volumes != g['bader_volumes']))
+    print(f"c1 DEFAULT via Bader.__call__: {differ} of {rho.size} bader_volumes voxels differ")
+
+
+def test_bader_call_speed_profile_c1(installed):
+    """the reference's `speed` profile: ongrid, atoms assigned first, then
+    refine ('changed', 3) on atoms_volumes (interface.py:412-414) -- every piece is
+    bit-exact, so the labels must be identical"""
+    g = load('c1_speed')
+    rho = density_from_tables(g['tx'], g['ty'], g['tz'])
+    b = make_bader(installed, {'charge': rho}, g, profile='speed')
+    assert not hasattr(b, 'bader_volumes')       # del(self.bader_volumes), interface.py:414
+    compare(b, g, labels_exact=True)
+
+
+def test_bader_call_reference_is_not_density_with_spin(installed):
+    """`reference is not density` (interface.py:136-137; the -ref flow of
+    entry_points.py:184-194): maxima, vacuum mask and refinement follow the reference,
+    the sums integrate charge and spin"""
+    g = load('ref_spin')
+    b = make_bader(installed, {'charge': g['charge'].copy(), 'spin': g['spin'].copy()}, g,
+                   reference=g['reference'].copy(), vacuum_tol=float(g['vacuum_tol']),
+                   spin_flag=True)
+    compare(b, g, labels_exact=False)
+    # the reference density really was the one analysed: the charge alone gives other volumes
+    b2 = make_bader(installed, {'charge': g['charge'].copy(), 'spin': g['spin'].copy()}, g,
+                    vacuum_tol=float(g['vacuum_tol']), spin_flag=True)
+    assert not np.array_equal(b2.bader_volumes, b.bader_volumes)
+
+
+def test_bader_call_config4_full_size(installed):
+    """BASELINE config 4 at FULL size (512x512x1024 slab, spin, vacuum) through the
+    unmodified Bader.__call__ against the reference's own output"""
+    g = load('c4_slab')
+    rho = density_from_tables(g['tx'], g['ty'], g['tz'])
+    spin = density_from_tables(g['sx'], g['ty'], g['tz'])
+    b = make_bader(installed, {'charge': rho, 'spin': spin}, g,
+                   vacuum_tol=float(g['vacuum_tol']), spin_flag=True)
+    compare(b, g, labels_exact=False)
+    differ = int(np.count_nonzero(b.bader_volumes != g['bader_volumes']))
+    print(f"c4 via Bader.__call__: {differ} of {rho.size} bader_volumes voxels differ")
+
+
+# ---- residency ---------------------------------------------------------------
+def _case():
+    from pybader_b200 import geometry as geo, synth
+    c = synth.case_c1(40)
+    rho, atoms = synth.make(c)
+    rho2 = rho + 0.35 * np.roll(rho, (7, 3, 11), axis=(0, 1, 2))
+    return c, rho, rho2, atoms, geo.distance_matrix(c['lattice'], rho.shape), \
+        geo.T_grad(c['lattice'], rho.shape), geo.voxel_volume(c['lattice'], rho.shape)
+
+
+def test_alternating_references_of_the_same_shape():
+    """a density that is resident in the CHARGE / SPIN slot must not be taken
+    for the reference in slot 0"""
+    from pybader_b200 import session, thread_handlers as th, utils as ut
+    session.close_all()
+    c, rho, rho2, atoms, dist, T, dV = _case()
+    z = lambda: np.zeros(rho.shape, np.int32)
+    mx1, v1 = th.bader_calc('ongrid', rho, z(), dist, T, 1)
+    session.close_all()
+    mx2, v2 = th.bader_calc('ongrid', rho2, z(), dist, T, 1)
+    assert not np.array_equal(v1, v2)
+    session.close_all()
+    # reference rho, then rho2 lands in the CHARGE slot through charge_sum, then the
+    # reference is switched to rho2 and back
+    a1 = th.bader_calc('ongrid', rho, z(), dist, T, 1)
+    q, v = np.zeros(len(a1[0])), np.zeros(len(a1[0]))
+    ut.charge_sum(q, v, dV, rho2, a1[1])
+    s = session.get(rho.shape)
+    up = s.uploads['density']
+    a2 = th.bader_calc('ongrid', rho2, z(), dist, T, 1)
+    assert s.uploads['density'] == up            # copied on the device, not uploaded again
+    a3 = th.bader_calc('ongrid', rho, z(), dist, T, 1)
+    np.testing.assert_array_equal(a2[1], v2)
+    np.testing.assert_array_equal(a2[0], mx2)
+    np.testing.assert_array_equal(a3[1], v1)
+    # refine and surface_distance read the array they are given as well
+    w1, w2 = v1.copy(), v1.copy()
+    th.refine('neargrid', ('all', 1), rho2, w1, dist, T, 1)
+    session.close_all()
+    th.refine('neargrid', ('all', 1), rho2, w2, dist, T, 1)
+    np.testing.assert_array_equal(w1, w2)
+    session.close_all()
+
+
+def test_user_edit_of_bader_volumes_between_stages():
+    """an in-place edit of the label array the engine handed out -- at
+    voxels no sample would have hit -- must reach the next stage"""
+    from pybader_b200 import session, thread_handlers as th, utils as ut
+    session.close_all()
+    c, rho, _, atoms, dist, T, dV = _case()
+    mx, vol = th.bader_calc('ongrid', rho, np.zeros(rho.shape, np.int32), dist, T, 1)
+    n = len(mx)
+    q0, v0 = np.zeros(n), np.zeros(n)
+    ut.charge_sum(q0, v0, dV, rho, vol)
+    s = session.get(rho.shape)
+    up = s.uploads['labels']
+    q1, v1 = np.zeros(n), np.zeros(n)
+    ut.charge_sum(q1, v1, dV, rho, vol)          # untouched: still resident
+    assert s.uploads['labels'] == up
+    np.testing.assert_array_equal(q0, q1)
+    # the user masks three voxels (none of them on a 4096-stride sample)
+    idx = [(1, 2, 3), (17, 5, 29), (39, 39, 38)]
+    moved = {}
+    for i in idx:
+        moved[i] = (int(vol[i]), float(rho[i]))
+        vol[i] = -1
+    q2, v2 = np.zeros(n), np.zeros(n)
+    ut.charge_sum(q2, v2, dV, rho, vol)
+    assert s.uploads['labels'] == up + 1
+    exp_q, exp_v = q0.copy(), v0.copy()
+    for i, (l, r) in moved.items():
+        exp_q[l] -= r * dV
+        exp_v[l] -= dV
+    np.testing.assert_allclose(q2, exp_q, rtol=1e-12)
+    np.testing.assert_allclose(v2, exp_v, rtol=1e-12)
+    # and an edited density is a different density
+    rho_edit = rho.copy()
+    q3, v3 = np.zeros(n), np.zeros(n)
+    ut.charge_sum(q3, v3, dV, rho_edit, vol)
+    np.testing.assert_allclose(q3, q2, rtol=1e-15)
+    rho_edit[17, 5, 28] += 1.0
+    q4, v4 = np.zeros(n), np.zeros(n)
+    ut.charge_sum(q4, v4, dV, rho_edit, vol)
+    assert q4[vol[17, 5, 28]] == pytest.approx(q3[vol[17, 5, 28]] + dV, rel=1e-12)
+    session.close_all()
+
+
+def test_vacuum_assign_without_vacuum_moves_no_labels():
+    """no host scan and no label download when nothing is vacuum"""
+    from pybader_b200 import session, utils as ut
+    session.close_all()
+    c, rho, _, atoms, dist, T, dV = _case()
+    vol = np.zeros(rho.shape, np.int32)
+    s = session.get(rho.shape)
+    calls = []
+    orig = s.labels_to_host
+    s.labels_to_host = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    out, q, v = ut.vacuum_assign(rho, vol, np.float64(-1.0), rho, dV)
+    assert out is vol and q == 0.0 and v == 0.0 and not calls and not vol.any()
+    assert s.uploads['labels'] == 0
+    out, q, v = ut.vacuum_assign(rho, vol, np.float64(rho.mean()), rho, dV)
+    assert calls and (vol == -1).sum() == (rho <= rho.mean()).sum()
+    assert v == pytest.approx((rho <= rho.mean()).sum() * dV, rel=1e-12)
+    session.close_all()

@@ -451,6 +451,87 @@ def test_config2_full_size_ongrid_bit_exact(th, ut, orc):
     np.testing.assert_array_equal(vol, rvol)
 
 
+def test_config3_full_size_vs_oracle(th, ut, orc):
+    """BASELINE config 3 at FULL size (triclinic 128-atom cell 360x360x480, vacuum_tol 1e-3,
+    neargrid + refine ('changed', 2)) against the reference-pinned oracle on the same bytes
+    (the density is generated on the device and downloaded; ~1 min of oracle on one host
+    core).  Same bars and the same vacuum-quirk accounting as test_neargrid_vs_oracle."""
+    from pybader_b200 import geometry as geo, session, synth
+    from pybader_b200.engine import Engine
+    session.close_all()
+    c = synth.case_triclinic((360, 360, 480), n_atoms=128, seed=1234)
+    shape = c['shape']
+    e = Engine(shape)
+    e.synth_general(0, c['lattice'], c['frac_atoms'], c['amps'], c['sigmas'])
+    rho = e.download_density(0)
+    e.close()
+    s = dict(name='c3_full', rho=rho, lattice=c['lattice'], vacuum_tol=1e-3,
+             dist_mat=geo.distance_matrix(c['lattice'], shape), T_grad=geo.T_grad(c['lattice'], shape),
+             voxel_volume=geo.voxel_volume(c['lattice'], shape))
+    mode = ('changed', 2)
+    v0 = gpu_fresh(ut, s)
+    r0 = oracle_fresh(orc, s)
+    np.testing.assert_array_equal(v0, r0)
+    mx, vol = th.bader_calc('neargrid', rho, v0, s['dist_mat'], s['T_grad'], 1)
+    th.refine('neargrid', mode, rho, vol, s['dist_mat'], s['T_grad'], 1)
+    hist = list(th.refine.last_history)
+    rmx, rvol = orc.bader_calc('neargrid', rho, r0, s['dist_mat'], s['T_grad'])
+    orc.refine('neargrid', mode, rho, rvol, s['dist_mat'], s['T_grad'])
+    key = lambda m: sorted(map(tuple, m.tolist()))
+    assert key(mx) == key(rmx)
+    assert vol.dtype == rvol.dtype                      # int16: >= 128 maxima
+    order = {tuple(m): i for i, m in enumerate(rmx.tolist())}
+    perm = np.array([order[tuple(m)] for m in mx.tolist()])
+    n = mx.shape[0]
+    quirk = (vol == -1) & (rvol >= 0)                   # SURVEY A.5, see test_neargrid_vs_oracle
+    assert quirk.sum() <= 1e-5 * vol.size
+    assert not ((vol >= 0) & (rvol == -1)).any()
+    vol_cmp = vol.copy()
+    vol_cmp[quirk] = np.argsort(perm)[rvol[quirk]]
+    ndiff = check_neargrid(vol_cmp, mx, rvol, rmx, rho, orc, s['name'])
+    q, v, rq, rv = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    ut.charge_sum(q, v, s['voxel_volume'], rho, vol_cmp)
+    orc.charge_sum(rq, rv, s['voxel_volume'], rho, rvol)
+    np.testing.assert_allclose(q, rq[perm], rtol=REL_TOL, atol=1e-9)
+    np.testing.assert_allclose(v, rv[perm], rtol=REL_TOL)
+    print(f"config 3 (360x360x480, {n} maxima): {ndiff} of {vol.size} voxels differ from the reference "
+          f"path, {int(quirk.sum())} vacuum voxels relabelled by the reference only; refine history {hist}")
+    session.close_all()
+
+
+def test_raw_neargrid_labels_vs_reference_raw_labels(th, ut):
+    """bader_calc('neargrid') WITHOUT refinement against the real reference's
+    raw (scan-order dependent) labels on BASELINE config 1.  The reference's raw labels differ
+    from its own refined labels on 0.1-0.3 % of voxels (all on Bader surfaces); this
+    engine's bader_calc returns the refinement fixed point, so its agreement with the raw labels
+    is bounded by the same figure.  Measured and reported here; the 99.9 % bar of the north star
+    is met against the refined result (test_config1_* in test_config1_reference.py)."""
+    import hashlib
+    import os
+    from pybader_b200 import geometry as geo, synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden_c1', 'c1_96.npz')
+    with np.load(path) as z:
+        g = {k: z[k] for k in z.files}
+    c = synth.case_c1(96)
+    rho, _ = synth.make(c)
+    if not np.array_equal(np.frombuffer(hashlib.sha256(rho.tobytes()).digest(), dtype=np.uint8),
+                          g['rho_sha256']):
+        pytest.skip("this CPU's exp() gives other density bytes than the golden run")
+    dist, T = geo.distance_matrix(c['lattice'], rho.shape), geo.T_grad(c['lattice'], rho.shape)
+    mx, vol = th.bader_calc('neargrid', rho, np.zeros(rho.shape, np.int32), dist, T, 1)
+    np.testing.assert_array_equal(mx, g['neargrid_maxima'])
+    raw = g['neargrid_raw_labels']
+    refined = g['neargrid_refined_labels']
+    d_raw = int(np.count_nonzero(vol != raw))
+    d_ref = int(np.count_nonzero(vol != refined))
+    own = int(np.count_nonzero(raw != refined))
+    print(f"raw bader_calc('neargrid') on config 1: {d_raw} of {vol.size} voxels differ from the "
+          f"reference's raw labels ({1 - d_raw / vol.size:.6f} agree), {d_ref} from its refined labels; "
+          f"the reference's raw and refined labels differ on {own}")
+    assert d_ref <= 1e-3 * vol.size
+    assert d_raw <= own + 1e-3 * vol.size      # no further from the raw labels than refinement itself
+
+
 # ------------------------------------------------ properties at size -------
 def test_properties_256(th, ut):
     """size-independent properties on a 256^3 rocksalt cell (BASELINE config 2

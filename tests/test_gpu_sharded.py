@@ -1,5 +1,6 @@
-"""2-GPU check of the sharded path against the single-GPU path (needs >= 2
-visible GPUs; skipped otherwise)."""
+"""Sharded path against the single-GPU path on 2, 4 and 8 GPUs (SURVEY.md 8e "Check":
+P-GPU labels bit-identical to 1-GPU labels at sizes one GPU holds).  Each case needs that
+many visible GPUs and is skipped otherwise: run with `gpurun --gpus N`."""
 import os
 import socket
 import sys
@@ -19,16 +20,33 @@ def _free_port():
     return p
 
 
-def _case():
+CASES = {
+    # name: (world, shape, halo)
+    'w2_toy_halo8': (2, (96, 64, 80), 8),
+    'w2_512_halo4': (2, (512, 256, 256), 4),      # the bench's halo
+    'w4_512_halo4': (4, (512, 256, 256), 4),
+    'w8_512_halo4': (8, (512, 256, 256), 4),
+}
+
+
+def _case(shape):
     from pybader_b200 import geometry as geo, synth
-    c = synth.case_rocksalt(96, cells=2, offset=0.13, a=5.64)
-    c['shape'] = (96, 64, 80)
-    rho, atoms = synth.make(c)
+    if shape == (96, 64, 80):
+        c = synth.case_rocksalt(96, cells=2, offset=0.13, a=5.64)
+        c['shape'] = shape
+        rho, atoms = synth.make(c)
+    else:
+        # jittered lattice sites in an orthorhombic cell: separable, generated from tables
+        c = synth.case_lattice_sites(shape, (4, 2, 2), (20.0, 10.0, 10.0), seed=11)
+        tx, ty, tz = synth.separable_tables(c)
+        rho = np.zeros(shape)
+        for a in range(tx.shape[0]):
+            rho += (tx[a][:, None, None] * ty[a][None, :, None]) * tz[a][None, None, :]
     return rho, geo.distance_matrix(c['lattice'], rho.shape), geo.T_grad(c['lattice'], rho.shape), \
         geo.voxel_volume(c['lattice'], rho.shape)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, shape, halo):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -39,8 +57,8 @@ def _worker(rank, world, port, out):
                             device_id=torch.device('cuda', rank))
     try:
         from pybader_b200.sharded import Comm, ShardedBader, SlabBackend
-        rho, dm, T, dV = _case()
-        sb = ShardedBader(rho.shape, Comm(), lambda ws, h: SlabBackend(ws, h, device=rank), halo=8)
+        rho, dm, T, dV = _case(shape)
+        sb = ShardedBader(rho.shape, Comm(), lambda ws, h: SlabBackend(ws, h, device=rank), halo=halo)
         win = np.ascontiguousarray(rho[sb.window_x])
         sb.backend.check(sb.backend.lib.bdr_upload_density(sb.backend.h, 0, win.ctypes.data))
         sb.backend.clear_labels()
@@ -63,16 +81,18 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_gpu_labels_equal_single_gpu(tmp_path):
+@pytest.mark.parametrize('name', list(CASES))
+def test_sharded_labels_equal_single_gpu(tmp_path, name):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    world, shape, halo = CASES[name]
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     from pybader_b200 import build
     build.build()
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shape, halo), nprocs=world, join=True)
     from pybader_b200.engine import Engine, LABELS_BADER
-    rho, dm, T, dV = _case()
+    rho, dm, T, dV = _case(shape)
     e = Engine(rho.shape)
     e.upload_density(0, rho)
     e.clear_labels()
@@ -89,7 +109,7 @@ def test_two_gpu_labels_equal_single_gpu(tmp_path):
     qn, vn = np.zeros(mxn.shape[0]), np.zeros(mxn.shape[0])
     e.charge_sum(LABELS_BADER, 0, dV, qn, vn)
     e.close()
-    parts = [np.load(os.path.join(str(tmp_path), f'r{r}.npz')) for r in range(2)]
+    parts = [np.load(os.path.join(str(tmp_path), f'r{r}.npz')) for r in range(world)]
     np.testing.assert_array_equal(parts[0]['maxima'], mx)
     np.testing.assert_array_equal(np.concatenate([p['lab_on'] for p in parts]), ref_on)
     np.testing.assert_array_equal(np.concatenate([p['lab_ng'] for p in parts]), ref_ng)
@@ -102,5 +122,8 @@ def test_two_gpu_labels_equal_single_gpu(tmp_path):
     assert int(parts[0]['hist2'][0][1]) <= max(2, 1e-4 * ref_nn.size)
     lab_nn = np.concatenate([p['lab_nn'] for p in parts])
     assert np.mean(lab_nn == ref_nn) >= 0.999
+    print(f"{name}: ongrid and ongrid+refine(all,-1) labels bit-identical to 1 GPU over {world} ranks "
+          f"({len(hist)} passes); neargrid: {int(np.count_nonzero(lab_nn != ref_nn))} of {ref_nn.size} "
+          f"voxels differ")
     np.testing.assert_allclose(parts[0]['q2'], qn, rtol=1e-6)
     np.testing.assert_allclose(parts[0]['v2'], vn, rtol=1e-6)
