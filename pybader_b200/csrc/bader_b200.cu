@@ -488,8 +488,11 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
     if (n == 0) return 0;
     if (sticky_mode != 0) {
         // conservative passes inside bader_calc('neargrid') skip the density half:
-        // a candidate that is a maximum merely stays listed (its trace ends on
-        // itself at once) and non-interior, which is the safe side
+        // a candidate that is a maximum stays listed; the maxima of the stencil pass
+        // (c->roots) are marked interior instead and the trace kernels skip them
+        if (c->n_max > 0 && c->roots)
+            LAUNCH(c, BDR_K_EDGE_CONFIRM, k_mark_interior, blocks_for(c->n_max, 128), 128, 0, c->known,
+                   c->roots, c->n_max);
         *edges = n;
         return 0;
     }
@@ -553,6 +556,10 @@ static int incremental_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *qu
     if (nq > 0)
         LAUNCH(c, BDR_K_EDGE_CHECK, k_inc_dilate, blocks_for(nq * 27, 128), 128, 0, c->known, c->g,
                c->list, nq);
+    // maxima stay interior through the conservative rounds (see k_mark_interior)
+    if (c->n_max > 0 && c->roots)
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_mark_interior, blocks_for(c->n_max, 128), 128, 0, c->known, c->roots,
+               c->n_max);
     c->list_n = nq;
     *queued = nq;
     return 0;
