@@ -366,6 +366,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=0, help='override: cubic N^3 single-GPU grid')
+    ap.add_argument('--workload', default='target', choices=['target', 'c3', 'c4'],
+                    help='target: the 1024^3 north-star cell (default); c3 / c4: BASELINE configs 3 / 4 '
+                         '(extra lines kept under profiles/)')
     ap.add_argument('--cpu-sample', type=int, default=256)
     ap.add_argument('--ref-sample', type=int, default=160, help='port fallback: cell edge')
     ap.add_argument('--ref-spacing', type=float, default=0.0,
@@ -393,19 +396,38 @@ def main():
     build.build()
     from pybader_b200.engine import Engine, LABELS_BADER
 
-    shape = (args.size,) * 3 if args.size else SHAPES[1]
+    vac_tol = None
+    if args.workload == 'c3':
+        # BASELINE config 3: triclinic 128-atom cell 360x360x480, vacuum_tol 1e-3
+        case = synth.case_triclinic((360, 360, 480), n_atoms=128, seed=1234)
+        shape, vac_tol = case['shape'], 1e-3
+        name = "BASELINE config 3: 360x360x480 triclinic 128-atom cell, vacuum_tol 1e-3, neargrid + refine('changed',2)"
+    elif args.workload == 'c4':
+        # BASELINE config 4: 512x512x1024 orthorhombic slab with vacuum (the spin density rides along
+        # in the sums only, which are outside the metric's path)
+        case = synth.case_slab((512, 512, 1024), n_atoms=64, seed=4321)
+        shape, vac_tol = case['shape'], 1e-3
+        name = "BASELINE config 4: 512x512x1024 slab with vacuum, vacuum_tol 1e-3, neargrid + refine('changed',2)"
+    else:
+        shape = (args.size,) * 3 if args.size else SHAPES[1]
+        case, cells = workload_case(shape)
+        name = workload_name(shape)
     N = int(np.prod(shape))
-    case, cells = workload_case(shape)
     dist = geo.distance_matrix(case['lattice'], shape)
     T = geo.T_grad(case['lattice'], shape)
     dV = geo.voxel_volume(case['lattice'], shape)
     e = Engine(shape, device=local)
-    e.synth_separable(0, *synth.separable_tables(case))
+    if args.workload == 'c3':
+        e.synth_general(0, case['lattice'], case['frac_atoms'], case['amps'], case['sigmas'])
+    else:
+        e.synth_separable(0, *synth.separable_tables(case))
     n_atoms = len(case['amps'])
     mode = ('changed', 2)
 
     def step():
         e.clear_labels(LABELS_BADER)
+        if vac_tol is not None:
+            e.vacuum_assign(vac_tol, dV)       # Bader.volumes_init (interface.py:449-469)
         mx = e.bader_calc('neargrid', dist, T)
         hist = e.refine(LABELS_BADER, mode[0], mode[1], dist, T)
         return mx, hist
@@ -449,13 +471,13 @@ def main():
         from pybader_b200._lib import check
         check(e.lib.bdr_download_density(e.h, 0, host_rho.ctypes.data))
         cap = max(1 << 12, 2 * n_max)
-        e.run(host_rho, None, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
+        e.run(host_rho, vac_tol, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
               want_sums=False, out_labels=host_lab)
         e.synchronize()
         clocks.active = True
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e.run(host_rho, None, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
+            e.run(host_rho, vac_tol, dV, 'neargrid', mode[0], mode[1], dist, T, ldt, cap,
                   want_sums=False, out_labels=host_lab)
         e.synchronize()
         dt = (time.perf_counter() - t0) / args.steps
@@ -463,7 +485,36 @@ def main():
         e2e = {"value": N / dt, "unit": UNIT, "h2d_bytes_per_step": N * 8,
                "d2h_bytes_per_step": N * ldt.itemsize + n_max * 24, "ms_per_step": dt * 1e3,
                "api": "bdr_run (C ABI, pinned host density in, narrowed labels + maxima out)"}
+        # second figure: the path the unmodified `Bader` object drives -- thread_handlers.bader_calc
+        # + thread_handlers.refine with ordinary (pageable) numpy arrays, a fresh session per step
+        # like a fresh Bader.__call__: content hash + upload of the density, fresh int32 volumes
+        # (interface.py:456-457), narrowed labels back, refine's labels back if anything changed
+        from pybader_b200 import session, thread_handlers as th, utils as ut
+        rho_np = np.array(host_rho)          # pageable copy
         del host_rho, host_lab
+
+        def handler_step():
+            session.close_all()
+            vol = np.zeros(shape, dtype=ut.dtype_calc(-N))
+            if vac_tol is not None:
+                vol, _, _ = ut.vacuum_assign(rho_np, vol, np.float64(vac_tol), rho_np, dV)
+            mx_, vol = th.bader_calc('neargrid', rho_np, vol, dist, T, 1)
+            th.refine('neargrid', mode, rho_np, vol, dist, T, 1)
+            return vol
+
+        e.close()
+        handler_step()
+        hsteps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(hsteps):
+            vol_h = handler_step()
+        dth = (time.perf_counter() - t0) / hsteps
+        e2e["handlers"] = {"value": N / dth, "unit": UNIT, "ms_per_step": dth * 1e3, "steps": hsteps,
+                           "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * vol_h.dtype.itemsize,
+                           "api": "pybader_b200.thread_handlers.bader_calc + refine (the names "
+                                  "pybader.interface binds), pageable numpy arrays, fresh session per step"}
+        session.close_all()
+        del rho_np, vol_h
 
     clock_info = clocks.stop()      # sampled through both timed regions (device steps and e2e)
     cpu = None if args.no_cpu else cpu_baseline_leg(args.cpu_sample, args.ref_port)
@@ -472,7 +523,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(shape), "atoms": n_atoms, "maxima": n_max,
+        "config": {"workload": name, "atoms": n_atoms, "maxima": n_max,
                    "method": "neargrid", "refine_method": "neargrid", "refine_mode": list(mode),
                    "l2": "inputs (8 B/voxel density) are far larger than the 126 MB L2; no flush",
                    "parallelism": "1 GPU"},

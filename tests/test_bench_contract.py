@@ -8,20 +8,42 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
-                          '--steps', '1', '--warmup', '1', '--ref-sample', '40'],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert out.returncode == 0, out.stderr[-2000:]
-    d = json.loads(out.stdout.strip().splitlines()[-1])
+def _check_reference_line(d, kind):
     assert d['impl'] == 'reference' and d['metric'] == 'neargrid+refine voxels/s'
     assert d['unit'] == 'voxels/s' and d['higher_is_better'] is True and d['n_gpus'] == 1
     assert d['value'] > 0 and d['steps'] == 1 and d['vs_baseline'] is None
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    assert cb['kind'] == kind and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
     assert d['e2e'] == {"value": d['value'], "unit": 'voxels/s', "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert '1024x1024x1024' in d['config']['workload']
+
+
+def test_reference_arm_line_port_fallback():
+    """the C port (what runs when pybader / numba cannot be imported on the box)"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '1', '--ref-sample', '40', '--ref-port'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    _check_reference_line(d, 'port')
+    assert 'not importable' in d['cpu_baseline']['sample']
+
+
+def test_reference_arm_line_real_pybader():
+    """the unmodified reference (numba thread handlers) when it is importable here"""
+    sys.path.insert(0, ROOT)
+    from baseline.refload import find_reference
+    if find_reference() is None:
+        import pytest
+        pytest.skip("no pybader in baseline/_ref or /root/reference")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '1', '--ref-spacing', '20'],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    _check_reference_line(d, 'reference')
+    assert 'unmodified pybader' in d['cpu_baseline']['sample'] and 'threads=' in d['cpu_baseline']['sample']
 
 
 def test_reference_arm_other_ranks_exit_quietly():
