@@ -201,6 +201,12 @@ int bdr_slab_roots(bdr_ctx *ctx, int32_t *host_out, int64_t cap);
 int bdr_slab_first_voxel(bdr_ctx *ctx, int64_t n_slots, int32_t *dev_out);
 /* slot codes -> global volume numbers through dev_rank[slot]                 */
 int bdr_slab_apply_rank(bdr_ctx *ctx, const int32_t *dev_rank);
+/* renumbering once the labels are final (volumes are numbered by their first voxel in
+ * C order, the reference's discovery order; utils.volume_offset utils.py:497-510):
+ * first owned voxel (window-linear, 0x7f7f7f7f if none) of every volume number, and
+ * labels >= 0 -> dev_lut[label] in place over the whole window                  */
+int bdr_slab_first_voxel_labels(bdr_ctx *ctx, int64_t n_labels, int32_t *dev_out);
+int bdr_slab_relabel(bdr_ctx *ctx, int which, const int32_t *dev_lut);
 /* one full edge pass / one Jacobi trace launch over the owned edge voxels;
  * escaped counts trajectories that left the trusted planes of the window    */
 int bdr_edge_pass(bdr_ctx *ctx, int which, int64_t *edges);

@@ -57,6 +57,8 @@ SIGNATURES = {
     "bdr_slab_roots": ([_p, _p, _i64], _int),
     "bdr_slab_first_voxel": ([_p, _i64, _p], _int),
     "bdr_slab_apply_rank": ([_p, _p], _int),
+    "bdr_slab_first_voxel_labels": ([_p, _i64, _p], _int),
+    "bdr_slab_relabel": ([_p, _int, _p], _int),
     "bdr_slab_first_pass": ([_p, _int, ctypes.POINTER(_i64)], _int),
     "bdr_slab_trace": ([_p, _int, _p, _p, _int, ctypes.POINTER(_i64)], _int),
     "bdr_slab_requeue": ([_p, _int, _p, _i64, ctypes.POINTER(_i64)], _int),

@@ -139,6 +139,7 @@ static int ensure_sums(bdr_ctx *c, int64_t n) {
 }
 static int ensure_slots(bdr_ctx *c, int64_t n) {
     if (c->slots_cap >= n) return 0;
+    c->maxima_fresh[0] = c->maxima_fresh[1] = false;   // c->roots goes away
     for (int32_t **p : {&c->roots, &c->minidx, &c->rank}) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -497,6 +498,27 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
         return 0;
     }
     // density half of the classification: drop the candidates that are maxima
+    if (c->halo == 0 && c->maxima_fresh[which] && c->roots && !getenv("BDR_CONFIRM_ALL")) {
+        // the maxima are known (k_edge_confirm_roots): test those, not every candidate
+        int64_t nf = 0;
+        if (c->n_max > 0) {
+            TRY(ensure(&c->list3, &c->list3_cap, c->n_max));
+            TRY(zero_counter(c, CNT_CENTRES));
+            LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_confirm_roots, blocks_for(c->n_max, 128), 128, 0,
+                   rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->g, c->ebits, c->nzw, c->roots,
+                   c->n_max, c->d_cnt + CNT_CENTRES, c->list3, c->list3_cap);
+            TRY(read_counters(c));
+            nf = (int64_t)c->h_cnt[CNT_CENTRES];
+        }
+        *edges = n - nf;
+        if (nf > 0) {
+            LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_fix_clear, blocks_for(nf, 128), 128, 0, c->ebits, c->g,
+                   c->nzw, (int32_t *)nullptr, c->list3, nf);
+            LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_fix_known, blocks_for(nf * 27, 128), 128, 0, c->ebits,
+                   c->vbits, c->known, c->g, c->nzw, (int32_t *)nullptr, c->list3, nf);
+        }
+        return 0;   // the maxima stay in the list; its consumers skip entries with known != -2
+    }
     TRY(ensure(&c->list3, &c->list3_cap, 4096));
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(zero_counter(c, CNT_NEWEDGE));
@@ -928,7 +950,7 @@ int bdr_create(int device, int64_t nx, int64_t ny, int64_t nz, bdr_ctx **out) {
     CU(cudaSetDevice(device));
     bdr_ctx *c = new bdr_ctx();
     c->device = device;
-    c->g = Grid{(int)nx, (int)ny, (int)nz};
+    c->g = make_grid((int)nx, (int)ny, (int)nz);
     c->N = N;
     c->own_lo = 0;
     c->own_hi = N;
@@ -1048,6 +1070,25 @@ int bdr_slab_apply_rank(bdr_ctx *c, const int32_t *dev_rank) {
     LAUNCH(c, BDR_K_RELABEL, k_relabel_slots, blocks_for(c->N, 1024), 256, 0,
            c->labels[BDR_LABELS_BADER], c->N, dev_rank);
     c->vac_mode = VAC_LABELS;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_slab_first_voxel_labels(bdr_ctx *c, int64_t n_labels, int32_t *dev_out) {
+    TRY(check(c));
+    if (n_labels <= 0) return 0;
+    CU(cudaMemsetAsync(dev_out, 0x7f, (size_t)n_labels * sizeof(int32_t), c->stream));
+    LAUNCH(c, BDR_K_FIRST, k_first_voxel_labels, blocks_for(c->own_hi - c->own_lo, 1024), 256, 0,
+           c->labels[BDR_LABELS_BADER], (int)c->own_lo, (int)c->own_hi, dev_out, (int)n_labels);
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_slab_relabel(bdr_ctx *c, int which, const int32_t *dev_lut) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_slab_relabel: bad label set");
+    LAUNCH(c, BDR_K_RELABEL, k_relabel_lut, blocks_for(c->N, 1024), 256, 0, c->labels[which],
+           c->labels[which], c->N, dev_lut);
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1187,6 +1228,7 @@ int bdr_synchronize(bdr_ctx *c) {
 int bdr_upload_density(bdr_ctx *c, int which, const double *host) {
     TRY(check(c));
     if (which < 0 || which > 2 || !host) return fail_msg("bdr_upload_density: bad argument");
+    if (which == BDR_RHO_REFERENCE) c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     TRY(ensure_rho(c, which));
     CU(cudaMemcpyAsync(c->rho[which], host, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice,
                        c->stream));
@@ -1208,6 +1250,7 @@ int bdr_alias_density(bdr_ctx *c, int which, int of) {
     TRY(check(c));
     if (which < 0 || which > 2 || of < 0 || of > 2 || which == of)
         return fail_msg("bdr_alias_density: bad argument");
+    if (which == BDR_RHO_REFERENCE) c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     if (c->rho[which]) {
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(c->rho[which]);
@@ -1223,6 +1266,7 @@ int bdr_copy_density(bdr_ctx *c, int dst, int src) {
     const double *from = rho_ptr(c, src);
     if (!from) return fail_msg("bdr_copy_density: source slot is empty");
     if (c->rho[dst] == from) return 0;
+    if (dst == BDR_RHO_REFERENCE) c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     // (a dst that merely aliased src gets storage of its own here)
     TRY(ensure_rho(c, dst));
     CU(cudaMemcpyAsync(c->rho[dst], from, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -1233,6 +1277,7 @@ int bdr_copy_density(bdr_ctx *c, int dst, int src) {
 int bdr_clear_labels(bdr_ctx *c, int which) {
     TRY(check(c));
     if (which < 0 || which > 1) return fail_msg("bdr_clear_labels: bad argument");
+    c->maxima_fresh[which] = false;
     TRY(ensure_labels(c, which));
     CU(cudaMemsetAsync(c->labels[which], 0, (size_t)c->N * sizeof(int32_t), c->stream));
     if (which == BDR_LABELS_BADER) c->vac_mode = VAC_NONE;
@@ -1242,6 +1287,7 @@ int bdr_clear_labels(bdr_ctx *c, int which) {
 int bdr_upload_labels(bdr_ctx *c, int which, const void *host, int elem_size) {
     TRY(check(c));
     if (which < 0 || which > 1 || !host) return fail_msg("bdr_upload_labels: bad argument");
+    c->maxima_fresh[which] = false;
     TRY(ensure_labels(c, which));
     if (which == BDR_LABELS_BADER) c->vac_mode = VAC_LABELS;
     switch (elem_size) {
@@ -1288,6 +1334,7 @@ int bdr_vacuum_assign(bdr_ctx *c, double vac_tol, double voxel_volume, int which
     const double *ref = rho_ptr(c, BDR_RHO_REFERENCE);
     const double *dens = rho_ptr(c, which_density);
     if (!ref || !dens) return fail_msg("bdr_vacuum_assign: density not uploaded");
+    c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     TRY(ensure_labels(c, BDR_LABELS_BADER));
     TRY(ensure_sums(c, 2));
     CU(cudaMemsetAsync(c->d_sums, 0, sizeof(double), c->stream));
@@ -1322,6 +1369,8 @@ static int bader_calc_dev(bdr_ctx *c, int method, const double *dist_mat, const 
         return fail_msg("bdr_bader_calc: unknown method");
     if (method == BDR_METHOD_NEARGRID && !T_grad) return fail_msg("bdr_bader_calc: T_grad is null");
     const Weights W = make_weights(dist_mat);
+    const int vac_mode_at_entry = c->vac_mode;
+    c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     TRY(choose_seed(c, method, W));
     int64_t seeded = -1;
     if (host_density) TRY(upload_and_stencil_dev(c, host_density, W, &seeded));
@@ -1335,6 +1384,10 @@ static int bader_calc_dev(bdr_ctx *c, int method, const double *dist_mat, const 
         TRY(converge_dev(c, BDR_LABELS_BADER, W, T));
         TRY(number_slots_dev(c, false));
     }
+    // the stencil pass's maxima stay valid for the edge passes that follow as long as the
+    // reference density and the vacuum mask (a threshold of that density, or none) do
+    c->maxima_fresh[BDR_LABELS_BADER] = vac_mode_at_entry != VAC_LABELS;
+    c->maxima_fresh[BDR_LABELS_ATOMS] = false;
     c->vac_mode = VAC_LABELS;
     if (n_maxima) *n_maxima = c->n_max;
     CU(cudaStreamSynchronize(c->stream));
@@ -1422,6 +1475,8 @@ int bdr_assign_atoms(bdr_ctx *c, const double *maxima_cart, int64_t n_max, const
                        c->stream));
     LAUNCH(c, BDR_K_ASSIGN, k_relabel_lut, blocks_for(c->N, 1024), 256, 0, c->labels[BDR_LABELS_BADER],
            c->labels[BDR_LABELS_ATOMS], c->N, c->rank);
+    // the atom labels are the LUT image of the Bader labels: same vacuum voxels, same maxima
+    c->maxima_fresh[BDR_LABELS_ATOMS] = c->maxima_fresh[BDR_LABELS_BADER];
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1450,8 +1505,8 @@ int bdr_surface_distance(bdr_ctx *c, int which, const double *lattice, const dou
     CU(cudaMemcpyAsync(d_best, best.data(), (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice,
                        c->stream));
     CU(cudaMemsetAsync(d_seen, 0, (size_t)n_atoms * sizeof(unsigned long long), c->stream));
-    LAUNCH(c, BDR_K_SURFACE, k_surface_dist, blocks_for(c->list_n, 128), 128, 0, c->labels[which], c->g,
-           c->list, c->list_n, d_lat, d_atoms, d_best, d_seen, (int)n_atoms);
+    LAUNCH(c, BDR_K_SURFACE, k_surface_dist, blocks_for(c->list_n, 128), 128, 0, c->labels[which],
+           c->known, c->g, c->list, c->list_n, d_lat, d_atoms, d_best, d_seen, (int)n_atoms);
     CU(cudaMemcpyAsync(best.data(), d_best, (size_t)n_atoms * sizeof(double), cudaMemcpyDeviceToHost,
                        c->stream));
     CU(cudaMemcpyAsync(seen.data(), d_seen, (size_t)n_atoms * sizeof(unsigned long long),
@@ -1817,6 +1872,7 @@ int bdr_synth_separable(bdr_ctx *c, int which, const double *tx, const double *t
                         int64_t n_atoms) {
     TRY(check(c));
     if (which < 0 || which > 2) return fail_msg("bdr_synth_separable: bad slot");
+    if (which == BDR_RHO_REFERENCE) c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     TRY(ensure_rho(c, which));
     const int64_t nt = n_atoms * ((int64_t)c->g.nx + c->g.ny + c->g.nz);
     double *d_t = nullptr;
@@ -1837,6 +1893,7 @@ int bdr_synth_general(bdr_ctx *c, int which, const double *lattice, const double
                       const double *amps, const double *sigmas, int64_t n_atoms) {
     TRY(check(c));
     if (which < 0 || which > 2) return fail_msg("bdr_synth_general: bad slot");
+    if (which == BDR_RHO_REFERENCE) c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     TRY(ensure_rho(c, which));
     double *d = nullptr;
     CU(cudaMalloc((void **)&d, (size_t)(9 + 5 * n_atoms) * sizeof(double)));

@@ -43,7 +43,24 @@ inline int fail_msg(const std::string &m) {
 // grid geometry as the kernels see it (32-bit coordinates; N < 2^31 - 2^16)
 struct Grid {
     int nx, ny, nz;
+    // division of a linear voxel index (0 <= v < 2^31) by nz and ny as one 32x32 -> 64 bit
+    // multiply and a shift: floor(v / d) == (v * m) >> s with m = ceil(2^s / d), s = 31 +
+    // ceil(log2 d) (Granlund & Montgomery); unlin3 runs at every refill of the trace kernel
+    unsigned m_nz, m_ny;
+    int s_nz, s_ny;
 };
+inline void grid_magic(int d, unsigned *m, int *s) {
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    *s = 31 + l;
+    *m = (unsigned)(((1ull << *s) + (unsigned long long)d - 1) / (unsigned long long)d);
+}
+inline Grid make_grid(int nx, int ny, int nz) {
+    Grid g{nx, ny, nz, 0u, 0u, 0, 0};
+    grid_magic(nz, &g.m_nz, &g.s_nz);
+    grid_magic(ny, &g.m_ny, &g.s_ny);
+    return g;
+}
 __host__ __device__ inline int64_t gsize(const Grid &g) {
     return (int64_t)g.nx * g.ny * g.nz;
 }
@@ -87,7 +104,7 @@ struct bdr_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // host -> device chunks of bdr_run
     std::vector<cudaEvent_t> chunk_events;
-    bdr::Grid g{0, 0, 0};
+    bdr::Grid g{0, 0, 0, 0u, 0u, 0, 0};
     int64_t N = 0;
     int halo = 0;               // slab windows: extra x planes on each side (0 = periodic grid)
     int64_t own_lo = 0, own_hi = 0;  // owned linear index range
@@ -128,6 +145,7 @@ struct bdr_ctx {
     int32_t *minidx = nullptr; // first voxel (C order) of each slot's volume
     int32_t *rank = nullptr;   // slot -> volume number
     int64_t slots_cap = 0;
+    bool maxima_fresh[2] = {false, false};  // c->roots lists every density maximum the label set's edge pass can meet
     bool seed_f32 = false;         // the last stencil pass was the fp32-ranked seed (seed.cuh)
     int slab_seed_method = 0;      // BDR_OPT_SLAB_SEED_METHOD
     uint32_t *tile_keys = nullptr; // largest density of every stencil tile (resolve order)

@@ -166,7 +166,12 @@ class ShardedBader:
         if os.environ.get('BDR_DEBUG'):
             print(f"[sharded r{self.comm.rank}] {msg}", file=sys.stderr, flush=True)
 
-    def ongrid(self, dist_mat, method='ongrid'):
+    def ongrid(self, dist_mat, method='ongrid', provisional=False):
+        """seed + exit resolution + global numbering.  Volumes are numbered by their first
+        voxel in C order (the reference's discovery order).  With `provisional` they are
+        numbered by the voxel index of their maximum instead, without the first-voxel pass:
+        bader_calc('neargrid') numbers once its labels are final (`renumber`), like the
+        single-GPU path does."""
         be, H, P = self.backend, self.halo, self.plane
         self._dbg("seed")
         self._phase('seed')
@@ -214,22 +219,27 @@ class ShardedBader:
         # first owned voxel of every slot -> per root id
         self._dbg("numbering")
         self._phase('numbering')
-        first_w = be.first_voxel(n_slots).to(torch.int64)          # window-linear or NO_VOXEL
-        used = first_w != NO_VOXEL
-        if bool((G[used] == UNRESOLVED).any()):
-            raise RuntimeError("an owned voxel ends in an unresolved exit")
-        sel = used & (G >= 0)
-        gid_l = G[sel]
-        first_l = self._gid_of_window_index(first_w[sel])
-        gids = self.comm.allgather_padded(gid_l, -1)
-        firsts = self.comm.allgather_padded(first_l, -1)
-        keep = gids >= 0
-        gids, firsts = gids[keep], firsts[keep]
-        uniq, inv = torch.unique(gids, return_inverse=True)
-        first_u = torch.full((uniq.shape[0],), torch.iinfo(torch.int64).max, dtype=torch.int64,
-                             device=dev)
-        first_u.scatter_reduce_(0, inv, firsts, reduce='amin')
-        order = torch.argsort(first_u)              # volume number -> index into uniq
+        if provisional:
+            gids = self.comm.allgather_padded(torch.unique(G[G >= 0]), -1)
+            uniq = torch.unique(gids[gids >= 0])
+            order = torch.arange(uniq.shape[0], device=dev)
+        else:
+            first_w = be.first_voxel(n_slots).to(torch.int64)          # window-linear or NO_VOXEL
+            used = first_w != NO_VOXEL
+            if bool((G[used] == UNRESOLVED).any()):
+                raise RuntimeError("an owned voxel ends in an unresolved exit")
+            sel = used & (G >= 0)
+            gid_l = G[sel]
+            first_l = self._gid_of_window_index(first_w[sel])
+            gids = self.comm.allgather_padded(gid_l, -1)
+            firsts = self.comm.allgather_padded(first_l, -1)
+            keep = gids >= 0
+            gids, firsts = gids[keep], firsts[keep]
+            uniq, inv = torch.unique(gids, return_inverse=True)
+            first_u = torch.full((uniq.shape[0],), torch.iinfo(torch.int64).max, dtype=torch.int64,
+                                 device=dev)
+            first_u.scatter_reduce_(0, inv, firsts, reduce='amin')
+            order = torch.argsort(first_u)              # volume number -> index into uniq
         number_of = torch.empty_like(order)
         number_of[order] = torch.arange(order.shape[0], device=dev)
         # slot -> volume number (vacuum and unused exits -> -1)
@@ -248,6 +258,29 @@ class ShardedBader:
         self._dbg("ongrid done")
         mg = uniq[order].cpu().numpy()
         self.maxima = np.stack([mg // P, (mg // self.nz) % self.ny, mg % self.nz], axis=1)
+        return self.maxima
+
+    def renumber(self):
+        """number the volumes by the first voxel (C order) that carries them in the CURRENT
+        labels and reorder `maxima` accordingly (utils.volume_offset utils.py:497-510; the
+        reference's discovery order)"""
+        be = self.backend
+        n = int(self.maxima.shape[0])
+        if n == 0 or not hasattr(be, 'first_voxel_labels'):
+            return self.maxima
+        dev = be.labels().device
+        first_w = be.first_voxel_labels(n).to(torch.int64)
+        big = torch.iinfo(torch.int64).max
+        first_g = torch.where(first_w != NO_VOXEL, self._gid_of_window_index(first_w.clamp(max=be.N - 1)),
+                              torch.full_like(first_w, big))
+        if self.comm.world > 1:
+            dist.all_reduce(first_g, op=dist.ReduceOp.MIN, group=self.comm.group)
+        order = torch.argsort(first_g, stable=True)      # new number -> old number
+        lut = torch.empty(n, dtype=torch.int32, device=dev)
+        lut[order] = torch.arange(n, dtype=torch.int32, device=dev)
+        if not bool((order == torch.arange(n, device=dev)).all()):
+            be.relabel(lut)
+            self.maxima = self.maxima[order.cpu().numpy()]
         return self.maxima
 
     # ---- refinement ---------------------------------------------------------
@@ -288,8 +321,8 @@ class ShardedBader:
         `max_passes`; `self.settled` says whether the last one was quiet).
         A backend with `requeue` re-traces only the edges next to voxels that
         moved (like the single-GPU bader_calc); otherwise full passes."""
-        self.ongrid(dist_mat, 'neargrid')
         be = self.backend
+        self.ongrid(dist_mat, 'neargrid', provisional=hasattr(be, 'first_voxel_labels'))
         if not hasattr(be, 'requeue'):
             hist = self.refine(dist_mat, T_grad, max_passes)
             self.settled = not hist or hist[-1][1] == 0 or hist[-1][0] == 0
@@ -319,6 +352,8 @@ class ShardedBader:
             changed = self.comm.allreduce_sum(be.trace(dist_mat, T_grad, True), dev)
             hist.append((queued, changed))
             self._dbg(f"round {len(hist) - 1}: queued {queued} changed {changed}")
+        self._phase('rounds:number')
+        self.renumber()
         self._phase('rounds:halo')
         self.exchange_halo(lab)
         self._phase(None)
@@ -457,6 +492,17 @@ class SlabBackend:
         rank_lut = rank_lut.contiguous()
         torch.cuda.synchronize(self.device)
         self.check(self.lib.bdr_slab_apply_rank(self.h, rank_lut.data_ptr()))
+
+    def first_voxel_labels(self, n_labels):
+        out = torch.empty(max(n_labels, 1), dtype=torch.int32, device=self.device)
+        self._sync()
+        self.check(self.lib.bdr_slab_first_voxel_labels(self.h, int(n_labels), out.data_ptr()))
+        return out[:n_labels]
+
+    def relabel(self, lut):
+        lut = lut.contiguous()
+        self._sync()
+        self.check(self.lib.bdr_slab_relabel(self.h, 0, lut.data_ptr()))
 
     def edge_pass(self):
         torch.cuda.synchronize(self.device)
