@@ -212,6 +212,41 @@ int bdr_slab_relabel(bdr_ctx *ctx, int which, const int32_t *dev_lut);
 int bdr_edge_pass(bdr_ctx *ctx, int which, int64_t *edges);
 int bdr_trace_pass(bdr_ctx *ctx, int which, const double *dist_mat, const double *T_grad,
                    int64_t *changed, int64_t *escaped);
+/* the same pass keeping the list of relabelled voxels for bdr_slab_ec_* (want_list != 0) */
+int bdr_trace_pass_list(bdr_ctx *ctx, int which, const double *dist_mat, const double *T_grad,
+                        int want_list, int64_t *changed, int64_t *escaped);
+/* 'changed'-mode refinement across slabs: refinement.edge_check (refinement.py:409-508) cut
+ * into the phases between which the ranks exchange the halo planes of the known array
+ * (device pointer: bdr_device_ptr(ctx, 5)).  begin: the relabelled voxels of the last
+ * bdr_trace_pass_list that are still edges and maxima are centres at once.  round: one
+ * step of the centre selection in GLOBAL scan order over the owned relabelled voxels;
+ * repeat (exchanging known halos) until no rank reports undecided voxels.  finish (after
+ * a last exchange): re-classify the 27-neighbourhoods of all centres of the window,
+ * dilate, queue the new edges for the next trace; returns the new edges this rank owns. */
+int bdr_slab_ec_begin(bdr_ctx *ctx, int which);
+int bdr_slab_ec_round(bdr_ctx *ctx, int64_t *undecided);
+int bdr_slab_ec_finish(bdr_ctx *ctx, int which, int64_t *edges_owned);
+/* The round loops of a sharded run inside the library (one host decision per round instead
+ * of a Python protocol step per kernel): the library's own NCCL communicator over the slab
+ * ring (libnccl.so.2 is bound at run time).  comm_id: 128 bytes from ncclGetUniqueId on one
+ * rank, to be broadcast by the caller; comm_init: collective over all ranks.
+ * exchange: halo planes of label set 0 / 1 or of the known array (2) from their owners.
+ * rounds: bader_calc('neargrid') after the seed is numbered -- conservative first pass,
+ * then rounds around the relabelled voxels (own and the neighbours' on the adjacent halo
+ * planes) until nothing changes anywhere; history gets (edges or queued, changed) per round
+ * as global counts.  refine: thread_handlers.refine (thread_handlers.py:128-236) in mode
+ * BDR_MODE_ALL / BDR_MODE_CHANGED with the same history as bdr_refine on one GPU.       */
+int bdr_slab_comm_id(void *id_out_128_bytes);
+int bdr_slab_comm_init(bdr_ctx *ctx, int world, int rank, const void *id_128_bytes);
+int bdr_slab_exchange(bdr_ctx *ctx, int what);
+int bdr_slab_rounds(bdr_ctx *ctx, int which, const double *dist_mat, const double *T_grad,
+                    int64_t max_passes, int64_t *history, int64_t hist_cap, int64_t *n_hist,
+                    int *settled);
+int bdr_slab_refine(bdr_ctx *ctx, int which, int mode, int64_t iters, const double *dist_mat,
+                    const double *T_grad, int64_t *iters_run, int64_t *history, int64_t hist_cap);
+/* run every kernel and copy of this handle on `stream` (a cudaStream_t, e.g. the stream
+ * the caller's NCCL plumbing is ordered on) instead of the handle's own stream          */
+int bdr_set_stream(bdr_ctx *ctx, void *stream);
 
 /* bader_calc('neargrid') of a sharded run, cut where the ranks have to meet:
  * first_pass = full edge classification (starts the conservative interior

@@ -66,6 +66,16 @@ SIGNATURES = {
     "bdr_slab_ipc_attach": ([_p, _int, _int, _p, _p, _i64], _int),
     "bdr_edge_pass": ([_p, _int, ctypes.POINTER(_i64)], _int),
     "bdr_trace_pass": ([_p, _int, _p, _p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
+    "bdr_trace_pass_list": ([_p, _int, _p, _p, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),
+    "bdr_slab_ec_begin": ([_p, _int], _int),
+    "bdr_slab_ec_round": ([_p, ctypes.POINTER(_i64)], _int),
+    "bdr_slab_ec_finish": ([_p, _int, ctypes.POINTER(_i64)], _int),
+    "bdr_set_stream": ([_p, _p], _int),
+    "bdr_slab_comm_id": ([_p], _int),
+    "bdr_slab_comm_init": ([_p, _int, _int, _p], _int),
+    "bdr_slab_exchange": ([_p, _int], _int),
+    "bdr_slab_rounds": ([_p, _int, _p, _p, _i64, _p, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_int)], _int),
+    "bdr_slab_refine": ([_p, _int, _int, _i64, _p, _p, ctypes.POINTER(_i64), _p, _i64], _int),
     "bdr_selftest_div": ([_p, _i64, ctypes.c_uint64, ctypes.POINTER(_i64)], _int),
     "bdr_set_option": ([_p, _int, _i64], _int),
     "bdr_device_ptr": ([_p, _int, _pp], _int),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "bader_b200.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "common.cuh"),
-        os.path.join(HERE, "csrc", "seed.cuh"), os.path.join(HERE, "csrc", "edge.cuh"), os.path.join(HERE, "csrc", "parse.cuh"),
+        os.path.join(HERE, "csrc", "seed.cuh"), os.path.join(HERE, "csrc", "edge.cuh"), os.path.join(HERE, "csrc", "comm.cuh"), os.path.join(HERE, "csrc", "parse.cuh"),
         os.path.join(HERE, "csrc", "parse_num.h"), os.path.join(HERE, "csrc", "format.h"), os.path.join(HERE, "csrc", "pow5_table.h"),
         os.path.join(os.path.dirname(HERE), "include", "bader_b200.h")]
 SO = os.path.join(HERE, "libbader_b200.so")
@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-fmad=false",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-ldl",
 ]
 
 

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "seed.cuh"
 #include "edge.cuh"
+#include "comm.cuh"
 #include "parse.cuh"
 #include "format.h"
 
@@ -485,6 +486,7 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
         TRY(ensure(&c->defer, &c->defer_cap, nd));  // redo the pass with room for every deferred voxel
     }
     c->list_n = n;  // every candidate of the window; the trace kernel skips what it does not own
+    c->window_fresh = n_changed < 0 && sticky_mode == 0;
     *edges = 0;
     if (n == 0) return 0;
     if (sticky_mode != 0) {
@@ -498,7 +500,7 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
         return 0;
     }
     // density half of the classification: drop the candidates that are maxima
-    if (c->halo == 0 && c->maxima_fresh[which] && c->roots && !getenv("BDR_CONFIRM_ALL")) {
+    if (c->maxima_fresh[which] && c->roots && !getenv("BDR_CONFIRM_ALL")) {
         // the maxima are known (k_edge_confirm_roots): test those, not every candidate
         int64_t nf = 0;
         if (c->n_max > 0) {
@@ -510,12 +512,23 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
             TRY(read_counters(c));
             nf = (int64_t)c->h_cnt[CNT_CENTRES];
         }
-        *edges = n - nf;
         if (nf > 0) {
             LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_fix_clear, blocks_for(nf, 128), 128, 0, c->ebits, c->g,
                    c->nzw, (int32_t *)nullptr, c->list3, nf);
             LAUNCH(c, BDR_K_EDGE_CONFIRM, k_edge_fix_known, blocks_for(nf * 27, 128), 128, 0, c->ebits,
                    c->vbits, c->known, c->g, c->nzw, (int32_t *)nullptr, c->list3, nf);
+        }
+        if (c->halo == 0) {
+            *edges = n - nf;
+        } else {
+            // a slab reports the edges it owns: the edge bits left on its own planes
+            const int64_t row_words = (int64_t)c->g.ny * c->nzw;
+            const int64_t lo = (int64_t)c->halo * row_words, cnt = (int64_t)(c->g.nx - 2 * c->halo) * row_words;
+            TRY(zero_counter(c, CNT_NEWEDGE));
+            LAUNCH(c, BDR_K_EDGE_CONFIRM, k_popcount_words, 148 * 8, 256, 0, c->ebits + lo, cnt,
+                   c->d_cnt + CNT_NEWEDGE);
+            TRY(read_counters(c));
+            *edges = (int64_t)c->h_cnt[CNT_NEWEDGE];
         }
         return 0;   // the maxima stay in the list; its consumers skip entries with known != -2
     }
@@ -548,6 +561,7 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
 static int incremental_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *queued) {
     *queued = 0;
     c->list_n = 0;
+    c->window_fresh = false;
     if (n_changed == 0) return 0;
     const int64_t cap = std::min<int64_t>(n_changed * 27, c->N);
     TRY(ensure(&c->list3, &c->list3_cap, cap));
@@ -620,6 +634,13 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
     if (local_first) {
         win.xlo = c->halo;
         win.xhi = c->g.nx - c->halo - 1;
+        // an exact pass follows a full edge pass over the whole window on freshly exchanged
+        // labels: the classification of planes [2, W-3] equals the owners', and the labels read
+        // there belong to interior voxels or maxima, which no rank writes during the pass
+        if (c->window_fresh && !c->use_term) {
+            win.xlo = 2;
+            win.xhi = c->g.nx - 3;
+        }
     }
     if (!pv || local_first) {
         LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
@@ -691,29 +712,48 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
 
 // refinement.edge_check restated (see kernels.cuh K5).  Input: c->list2 holds
 // the voxels changed by the last trace (known == -2).  Output: c->list holds
-// the voxels to trace next (known == -2).
-static int edge_check_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *edges) {
+// the voxels to trace next (known == -2).  Three phases, so that the ranks of a
+// sharded run can exchange the known planes between them (bdr_slab_ec_*):
+//   begin   class-2 changed voxels are centres at once
+//   round   one step of the centre selection (repeat until nothing is undecided)
+//   finish  re-classify the 27-neighbourhoods of the centres, dilate, queue
+static int ec_begin_dev(bdr_ctx *c, int which, int64_t n_changed) {
+    if (n_changed == 0) return 0;
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_init, blocks_for(n_changed, 128), 128, 0,
+           rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, c->list2, n_changed);
+    return 0;
+}
+static int ec_round_dev(bdr_ctx *c, int64_t n_changed, int64_t *undecided) {
+    *undecided = 0;
+    if (n_changed == 0) return 0;
+    const PeerView *pv = static_cast<const PeerView *>(c->peer_view);
+    TRY(zero_counter(c, CNT_UNDECIDED));
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_round, blocks_for(n_changed, 128), 128, 0, c->known, c->g,
+           c->list2, n_changed, c->d_cnt + CNT_UNDECIDED, pv ? pv->x0w : 0, pv ? pv->NX : c->g.nx);
+    TRY(read_counters(c));
+    *undecided = (int64_t)c->h_cnt[CNT_UNDECIDED];
+    return 0;
+}
+static int ec_finish_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *edges) {
     *edges = 0;
     c->list_n = 0;
-    if (n_changed == 0) return 0;
+    c->window_fresh = false;   // only the neighbourhoods of the centres were re-classified
     const double *rho = rho_ptr(c, BDR_RHO_REFERENCE);
     const int32_t *lab = c->labels[which];
-    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_init, blocks_for(n_changed, 128), 128, 0, rho, lab, c->known,
-           c->g, c->list2, n_changed);
-    for (int round = 0;; ++round) {
-        TRY(zero_counter(c, CNT_UNDECIDED));
-        LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_round, blocks_for(n_changed, 128), 128, 0, c->known, c->g,
-               c->list2, n_changed, c->d_cnt + CNT_UNDECIDED);
-        TRY(read_counters(c));
-        if (c->h_cnt[CNT_UNDECIDED] == 0) break;
-        if (round > 1 << 20) return fail_msg("edge_check: centre selection did not converge");
-    }
-    TRY(ensure(&c->list3, &c->list3_cap, n_changed));
+    const int64_t plane = (int64_t)c->g.ny * c->g.nz;
+    const int64_t halo_cells = c->halo > 0 ? 2 * (int64_t)(c->halo - 1) * plane : 0;
+    if (n_changed == 0 && halo_cells == 0) return 0;
+    TRY(ensure(&c->list3, &c->list3_cap, n_changed + halo_cells + 1));
     TRY(zero_counter(c, CNT_CENTRES));
-    LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_collect_centres, blocks_for(n_changed, 128), 128, 0, c->known,
-           c->list2, n_changed, c->d_cnt + CNT_CENTRES, c->list3);
+    if (n_changed > 0)
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_collect_centres, blocks_for(n_changed, 128), 128, 0, c->known,
+               c->list2, n_changed, c->d_cnt + CNT_CENTRES, c->list3);
+    if (halo_cells > 0)
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_collect_halo, blocks_for(halo_cells, 256), 256, 0, c->known,
+               (int)plane, c->g.nx, c->halo, c->d_cnt + CNT_CENTRES, c->list3, c->list3_cap);
     TRY(read_counters(c));
     const int64_t nc = (int64_t)c->h_cnt[CNT_CENTRES];
+    if (nc == 0) return 0;
     TRY(ensure(&c->list, &c->list_cap, nc * 27 + nc));
     TRY(zero_counter(c, CNT_NEWEDGE));
     LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_classify, blocks_for(nc * 27, 128), 128, 0, rho, lab, c->known,
@@ -723,12 +763,27 @@ static int edge_check_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *edg
     if (ne > 0)
         LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_dilate, blocks_for(ne * 27, 128), 128, 0, c->known, c->g,
                c->list, ne);
+    TRY(zero_counter(c, CNT_EDGES));
     LAUNCH(c, BDR_K_EDGE_CHECK, k_ec_finish, blocks_for(ne + nc, 128), 128, 0, c->known, c->list, ne,
-           c->list3, nc, c->d_cnt + CNT_NEWEDGE, c->list_cap);
+           c->list3, nc, c->d_cnt + CNT_NEWEDGE, c->list_cap, (int)c->own_lo, (int)c->own_hi,
+           c->d_cnt + CNT_EDGES);
     TRY(read_counters(c));
     c->list_n = (int64_t)c->h_cnt[CNT_NEWEDGE];
-    *edges = ne;
+    *edges = (int64_t)c->h_cnt[CNT_EDGES];
     return 0;
+}
+static int edge_check_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *edges) {
+    *edges = 0;
+    c->list_n = 0;
+    if (n_changed == 0) return 0;
+    TRY(ec_begin_dev(c, which, n_changed));
+    for (int round = 0;; ++round) {
+        int64_t undecided = 0;
+        TRY(ec_round_dev(c, n_changed, &undecided));
+        if (undecided == 0) break;
+        if (round > 1 << 20) return fail_msg("edge_check: centre selection did not converge");
+    }
+    return ec_finish_dev(c, which, n_changed, edges);
 }
 
 // thread_handlers.refine (thread_handlers.py:144-236)
@@ -1046,11 +1101,16 @@ int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *
     if (!rho_ptr(c, BDR_RHO_REFERENCE)) return fail_msg("bdr_slab_seed: density not set");
     const Weights W = make_weights(dist_mat);
     int64_t n = 0;
+    const int vac_mode_at_entry = c->vac_mode;
+    c->maxima_fresh[0] = c->maxima_fresh[1] = false;
     TRY(choose_seed(c, c->slab_seed_method, W));
     TRY(stencil_dev(c, W, &n));
     TRY(resolve_dev(c, nullptr));
     CU(cudaStreamSynchronize(c->stream));
     c->n_max = n;
+    // c->roots now lists every maximum of the window's density off the two exit planes
+    // (whose classification no pass trusts): the exact edge passes test only those
+    c->maxima_fresh[BDR_LABELS_BADER] = vac_mode_at_entry != VAC_LABELS;
     if (n_real) *n_real = n;
     if (exit_base) *exit_base = exit_base_of(c);
     return 0;
@@ -1171,8 +1231,282 @@ int bdr_slab_requeue(bdr_ctx *c, int which, const int32_t *dev_extra, int64_t n_
     return 0;
 }
 
+// 'changed'-mode refinement across slabs (thread_handlers.py:201-205 ->
+// refinement.edge_check): the phases of edge_check_dev, cut where the ranks exchange the
+// halo planes of the known array
+int bdr_slab_ec_begin(bdr_ctx *c, int which) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !c->labels[which] || !c->known) return fail_msg("bdr_slab_ec_begin: bad state");
+    TRY(ec_begin_dev(c, which, c->last_changed));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int bdr_slab_ec_round(bdr_ctx *c, int64_t *undecided) {
+    TRY(check(c));
+    int64_t u = 0;
+    TRY(ec_round_dev(c, c->last_changed, &u));
+    if (undecided) *undecided = u;
+    return 0;
+}
+int bdr_slab_ec_finish(bdr_ctx *c, int which, int64_t *edges_owned) {
+    TRY(check(c));
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_slab_ec_finish: bad label set");
+    int64_t e = 0;
+    TRY(ec_finish_dev(c, which, c->last_changed, &e));
+    CU(cudaStreamSynchronize(c->stream));
+    if (edges_owned) *edges_owned = e;
+    return 0;
+}
+
+// ---- the sharded protocol's round loops, driven from the library (comm.cuh) --------
+int bdr_slab_comm_id(void *id_out) {
+    NcclApi *api = nccl_api();
+    if (!api) return fail_msg("bdr_slab_comm_id: libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    NC(api->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return 0;
+}
+
+int bdr_slab_comm_init(bdr_ctx *c, int world, int rank, const void *id_bytes) {
+    TRY(check(c));
+    if (c->halo == 0) return fail_msg("bdr_slab_comm_init: not a slab handle");
+    if (world < 1 || rank < 0 || rank >= world) return fail_msg("bdr_slab_comm_init: bad world / rank");
+    if (c->slab_comm) return fail_msg("bdr_slab_comm_init: already initialised");
+    SlabComm *sc = new SlabComm();
+    sc->world = world;
+    sc->rank = rank;
+    sc->prev = (rank + world - 1) % world;
+    sc->next = (rank + 1) % world;
+    if (world > 1) {
+        NcclApi *api = nccl_api();
+        if (!api) {
+            delete sc;
+            return fail_msg("bdr_slab_comm_init: libnccl.so.2 could not be loaded");
+        }
+        ncclUniqueId id;
+        memcpy(&id, id_bytes, sizeof id);
+        ncclResult_t r = api->CommInitRank(&sc->comm, world, id, rank);
+        if (r != ncclSuccess) {
+            delete sc;
+            return fail_msg(std::string("ncclCommInitRank failed: ") + api->GetErrorString(r));
+        }
+    }
+    const int64_t plane = (int64_t)c->g.ny * c->g.nz;
+    CU(cudaMalloc((void **)&sc->d_red, 8 * sizeof(unsigned long long)));
+    CU(cudaMallocHost((void **)&sc->h_red, 8 * sizeof(unsigned long long)));
+    CU(cudaMalloc((void **)&sc->plane_lo, (size_t)plane * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&sc->plane_hi, (size_t)plane * sizeof(int32_t)));
+    c->slab_comm = sc;
+    return 0;
+}
+
+int bdr_slab_exchange(bdr_ctx *c, int what) {
+    TRY(check(c));
+    SlabComm *sc = static_cast<SlabComm *>(c->slab_comm);
+    if (!sc) return fail_msg("bdr_slab_exchange: bdr_slab_comm_init has not run");
+    if (what == 0 || what == 1) {
+        if (!c->labels[what]) return fail_msg("bdr_slab_exchange: label set is empty");
+        return comm_halo_exchange(c, sc, c->labels[what], 4);
+    }
+    if (what == 2) {
+        if (!c->known) return fail_msg("bdr_slab_exchange: no edge pass has run");
+        return comm_halo_exchange(c, sc, c->known, 1);
+    }
+    return fail_msg("bdr_slab_exchange: bad selector");
+}
+
+// bader_calc('neargrid') of a sharded run after the seed is numbered: the conservative
+// rounds of converge_rounds, the ranks meeting at one all-reduce per decision
+int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
+                    int64_t max_passes, int64_t *history, int64_t hist_cap, int64_t *n_hist,
+                    int *settled) {
+    TRY(check(c));
+    SlabComm *sc = static_cast<SlabComm *>(c->slab_comm);
+    if (!sc) return fail_msg("bdr_slab_rounds: bdr_slab_comm_init has not run");
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_slab_rounds: bad label set");
+    const Weights W = make_weights(dist_mat);
+    const TGrad T = make_tgrad(T_grad);
+    const bool dbg = getenv("BDR_DEBUG") != nullptr && sc->rank == 0;
+    int64_t run = 0;
+    auto record = [&](int64_t a, int64_t b) {
+        if (history && run < hist_cap) {
+            history[2 * run] = a;
+            history[2 * run + 1] = b;
+        }
+        ++run;
+    };
+    int32_t *lab = c->labels[which];
+    const int64_t plane = (int64_t)c->g.ny * c->g.nz;
+    const int H = c->halo, Wp = c->g.nx;
+    TRY(comm_halo_exchange(c, sc, lab, 4));
+    int64_t e = 0;
+    TRY(edge_find_dev(c, which, &e, -1, 1));
+    c->last_changed = 0;
+    if (!c->term) CU(cudaMalloc((void **)&c->term, (size_t)c->N * sizeof(int32_t)));
+    CU(cudaMemsetAsync(c->term, 0xff, (size_t)c->N * sizeof(int32_t), c->stream));
+    c->use_term = true;
+    long long v[2] = {(long long)e, 0};
+    TRY(comm_allreduce(c, sc, 1, v));     // also the barrier before the first remote reads
+    const int64_t edges = v[0];
+    int64_t changed = 0;
+    if (edges > 0) {
+        int64_t ch = 0;
+        TRY(trace_dev(c, which, W, T, &ch, true));
+        c->last_changed = ch;
+        v[0] = ch;
+        TRY(comm_allreduce(c, sc, 1, v));
+        changed = v[0];
+    }
+    record(edges, changed);
+    if (dbg) fprintf(stderr, "[bdr slab] first pass: edges %lld changed %lld\n", (long long)edges, (long long)changed);
+    while (changed > 0 && run < max_passes) {
+        // the planes next to the owned slab, before and after the exchange: voxels a
+        // neighbour relabelled there count as changed here too
+        CU(cudaMemcpyAsync(sc->plane_lo, lab + (int64_t)(H - 1) * plane, (size_t)plane * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(sc->plane_hi, lab + (int64_t)(Wp - H) * plane, (size_t)plane * 4, cudaMemcpyDeviceToDevice, c->stream));
+        TRY(comm_halo_exchange(c, sc, lab, 4));
+        const int64_t need = c->last_changed + 2 * plane;
+        if (need > c->list2_cap) {
+            int32_t *grown = nullptr;
+            const int64_t cap = need + need / 4 + 1024;
+            CU(cudaMalloc((void **)&grown, (size_t)cap * sizeof(int32_t)));
+            if (c->last_changed)
+                CU(cudaMemcpyAsync(grown, c->list2, (size_t)c->last_changed * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->list2) cudaFree(c->list2);
+            c->list2 = grown;
+            c->list2_cap = cap;
+        }
+        TRY(zero_counter(c, CNT_CENTRES));
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_plane_diff, blocks_for(plane, 256), 256, 0, lab + (int64_t)(H - 1) * plane,
+               sc->plane_lo, (int)plane, (int)((H - 1) * plane), c->d_cnt + CNT_CENTRES, c->list2, c->last_changed,
+               c->list2_cap);
+        LAUNCH(c, BDR_K_EDGE_CHECK, k_plane_diff, blocks_for(plane, 256), 256, 0, lab + (int64_t)(Wp - H) * plane,
+               sc->plane_hi, (int)plane, (int)((Wp - H) * plane), c->d_cnt + CNT_CENTRES, c->list2, c->last_changed,
+               c->list2_cap);
+        TRY(read_counters(c));
+        const int64_t n = c->last_changed + (int64_t)c->h_cnt[CNT_CENTRES];
+        int64_t q = 0;
+        if (n * 2048 > c->N) {
+            TRY(edge_find_dev(c, which, &q, n, 2));
+        } else {
+            TRY(incremental_dev(c, which, n, &q));
+        }
+        TRY(filter_cached_dev(c));
+        v[0] = c->list_n;
+        TRY(comm_allreduce(c, sc, 1, v));
+        const int64_t queued = v[0];
+        int64_t ch = 0;
+        TRY(trace_dev(c, which, W, T, &ch, true));
+        c->last_changed = ch;
+        v[0] = ch;
+        TRY(comm_allreduce(c, sc, 1, v));
+        changed = v[0];
+        record(queued, changed);
+        if (dbg) fprintf(stderr, "[bdr slab] round %lld: queued %lld changed %lld\n", (long long)run - 1, (long long)queued, (long long)changed);
+    }
+    c->use_term = false;
+    c->last_changed = 0;
+    TRY(comm_halo_exchange(c, sc, lab, 4));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_hist) *n_hist = run;
+    if (settled) *settled = changed == 0;
+    return 0;
+}
+
+// thread_handlers.refine (thread_handlers.py:128-236) across the slabs: refine_dev with the
+// ranks meeting where the reference's serial code looks at the whole grid
+int bdr_slab_refine(bdr_ctx *c, int which, int mode, int64_t iters, const double *dist_mat,
+                    const double *T_grad, int64_t *iters_run, int64_t *history, int64_t hist_cap) {
+    TRY(check(c));
+    SlabComm *sc = static_cast<SlabComm *>(c->slab_comm);
+    if (!sc) return fail_msg("bdr_slab_refine: bdr_slab_comm_init has not run");
+    if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_slab_refine: bad label set");
+    if (mode != BDR_MODE_ALL && mode != BDR_MODE_CHANGED) return fail_msg("bdr_slab_refine: bad mode");
+    const Weights W = make_weights(dist_mat);
+    const TGrad T = make_tgrad(T_grad);
+    const bool chg_mode = mode == BDR_MODE_CHANGED;
+    const bool dbg = getenv("BDR_DEBUG") != nullptr && sc->rank == 0;
+    int64_t run = 0;
+    auto record = [&](int64_t a, int64_t b) {
+        if (history && run < hist_cap) {
+            history[2 * run] = a;
+            history[2 * run + 1] = b;
+        }
+        ++run;
+    };
+    if (iters_run) *iters_run = 0;
+    if (iters == 0) return 0;
+    int32_t *lab = c->labels[which];
+    c->use_term = false;
+    int64_t edges = 0, changed = 0;
+    for (int64_t it = 0; iters < 0 || it < iters; ++it) {
+        TRY(comm_halo_exchange(c, sc, lab, 4));
+        long long v[2] = {0, 0};
+        if (it == 0 || !chg_mode) {
+            int64_t e = 0;
+            TRY(edge_find_dev(c, which, &e));
+            v[0] = e;
+            TRY(comm_allreduce(c, sc, 1, v));      // the barrier before the remote reads, too
+            edges = v[0];
+            if (edges == 0) break;
+        } else {
+            TRY(ec_begin_dev(c, which, c->last_changed));
+            for (int round = 0;; ++round) {
+                TRY(comm_halo_exchange(c, sc, c->known, 1));
+                int64_t u = 0;
+                TRY(ec_round_dev(c, c->last_changed, &u));
+                v[0] = u;
+                TRY(comm_allreduce(c, sc, 1, v));
+                if (v[0] == 0) break;
+                if (round > 1 << 20) return fail_msg("edge_check: centre selection did not converge");
+            }
+            TRY(comm_halo_exchange(c, sc, c->known, 1));
+            int64_t e = 0;
+            TRY(ec_finish_dev(c, which, c->last_changed, &e));
+            v[0] = e;
+            TRY(comm_allreduce(c, sc, 1, v));
+            edges = v[0];
+        }
+        int64_t ch = 0;
+        TRY(trace_dev(c, which, W, T, &ch, chg_mode));
+        c->last_changed = chg_mode ? ch : 0;
+        v[0] = ch;
+        v[1] = c->escaped;
+        TRY(comm_allreduce(c, sc, 2, v));
+        changed = v[0];
+        if (v[1]) return fail_msg("bdr_slab_refine: a trajectory left the slab halo: raise the halo");
+        record(edges, changed);
+        if (dbg) fprintf(stderr, "[bdr slab] refine pass %lld: edges %lld changed %lld\n", (long long)it, (long long)edges, (long long)changed);
+        if (changed == 0) {
+            if (it == 0 && (iters < 0 || iters >= 2)) record(chg_mode ? 0 : edges, 0);
+            break;
+        }
+    }
+    c->last_changed = 0;
+    TRY(comm_halo_exchange(c, sc, lab, 4));
+    CU(cudaStreamSynchronize(c->stream));
+    if (iters_run) *iters_run = run;
+    return 0;
+}
+
+int bdr_set_stream(bdr_ctx *c, void *stream) {
+    TRY(check(c));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
+    c->stream = static_cast<cudaStream_t>(stream);
+    c->owns_stream = false;
+    return 0;
+}
+
 int bdr_trace_pass(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
                    int64_t *changed, int64_t *escaped) {
+    return bdr_trace_pass_list(c, which, dist_mat, T_grad, 0, changed, escaped);
+}
+
+int bdr_trace_pass_list(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
+                        int want_list, int64_t *changed, int64_t *escaped) {
     TRY(check(c));
     if (which < 0 || which > 1 || !c->labels[which]) return fail_msg("bdr_trace_pass: bad label set");
     if (!c->known) return fail_msg("bdr_trace_pass: run bdr_edge_pass first");
@@ -1180,7 +1514,8 @@ int bdr_trace_pass(bdr_ctx *c, int which, const double *dist_mat, const double *
     const Weights W = make_weights(dist_mat);
     const TGrad T = make_tgrad(T_grad);
     int64_t ch = 0;
-    TRY(trace_dev(c, which, W, T, &ch, false));
+    TRY(trace_dev(c, which, W, T, &ch, want_list != 0));
+    c->last_changed = want_list ? ch : 0;
     CU(cudaStreamSynchronize(c->stream));
     if (changed) *changed = ch;
     if (escaped) *escaped = c->escaped;
@@ -1209,12 +1544,21 @@ int bdr_destroy(bdr_ctx *c) {
     }
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     delete static_cast<PeerView *>(c->peer_view);
+    if (c->slab_comm) {
+        SlabComm *sc = static_cast<SlabComm *>(c->slab_comm);
+        if (sc->comm && nccl_api()) nccl_api()->CommDestroy(sc->comm);
+        if (sc->d_red) cudaFree(sc->d_red);
+        if (sc->h_red) cudaFreeHost(sc->h_red);
+        if (sc->plane_lo) cudaFree(sc->plane_lo);
+        if (sc->plane_hi) cudaFree(sc->plane_hi);
+        delete sc;
+    }
     for (auto e : c->pool) cudaEventDestroy(e);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     for (auto e : c->chunk_events) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->stream);
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }

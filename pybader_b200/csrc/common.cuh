@@ -102,12 +102,14 @@ struct ProfRec {
 struct bdr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;                 // false after bdr_set_stream
     cudaStream_t copy_stream = nullptr;      // host -> device chunks of bdr_run
     std::vector<cudaEvent_t> chunk_events;
     bdr::Grid g{0, 0, 0, 0u, 0u, 0, 0};
     int64_t N = 0;
     int halo = 0;               // slab windows: extra x planes on each side (0 = periodic grid)
     int64_t own_lo = 0, own_hi = 0;  // owned linear index range
+    bool window_fresh = false;  // known holds a full exact classification of the whole window (slab passes)
     int64_t escaped = 0;        // trajectories that left the trusted planes in the last trace
 
     double *rho[3] = {nullptr, nullptr, nullptr};
@@ -168,6 +170,7 @@ struct bdr_ctx {
 
     // sharded runs: device pointers of every rank's arrays (CUDA IPC), see kernels.cuh K4p
     void *peer_view = nullptr;      // bdr::PeerView, host copy
+    void *slab_comm = nullptr;      // bdr::SlabComm (comm.cuh): the library's own NCCL communicator
     std::vector<void *> ipc_opened;  // pointers to close on destroy
 
     bool prof = false;

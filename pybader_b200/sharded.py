@@ -114,6 +114,12 @@ class ShardedBader:
         # memory (CUDA IPC over NVLink); the CPU model backend has no such need
         if hasattr(self.backend, 'ipc_export'):
             self._attach_peers()
+        # the library's own NCCL communicator: the round loops of neargrid() and refine() then
+        # run inside libbader_b200.so (bdr_slab_rounds / bdr_slab_refine) with one host
+        # decision per round; BDR_PY_PROTOCOL=1 keeps the loops below (what the CPU tests drive)
+        self.native_loops = False
+        if hasattr(self.backend, 'comm_init') and not os.environ.get('BDR_PY_PROTOCOL'):
+            self._init_native_comm()
 
     def _attach_peers(self):
         be = self.backend
@@ -126,6 +132,16 @@ class ShardedBader:
             allh = mine
         be.ipc_attach(self.comm.world, self.comm.rank, bytes(allh.cpu().numpy().tobytes()),
                       self.bounds, self.shape[0])
+
+    def _init_native_comm(self):
+        be = self.backend
+        ident = torch.zeros(128, dtype=torch.uint8, device=be.device)
+        if self.comm.rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(be.comm_id()), dtype=torch.uint8))
+        if self.comm.world > 1:
+            dist.broadcast(ident, src=0, group=self.comm.group)
+        be.comm_init(self.comm.world, self.comm.rank, bytes(ident.cpu().numpy().tobytes()))
+        self.native_loops = True
 
     # ---- helpers -----------------------------------------------------------
     def _gid_of_window_index(self, widx):
@@ -278,38 +294,82 @@ class ShardedBader:
         order = torch.argsort(first_g, stable=True)      # new number -> old number
         lut = torch.empty(n, dtype=torch.int32, device=dev)
         lut[order] = torch.arange(n, dtype=torch.int32, device=dev)
-        if not bool((order == torch.arange(n, device=dev)).all()):
+        self._renumbered = not bool((order == torch.arange(n, device=dev)).all())
+        if self._renumbered:
             be.relabel(lut)
             self.maxima = self.maxima[order.cpu().numpy()]
         return self.maxima
 
+    def renumber_changed(self):
+        self.renumber()
+        return getattr(self, '_renumbered', False)
+
     # ---- refinement ---------------------------------------------------------
-    def refine(self, dist_mat, T_grad, iters=-1):
-        """full ('all'-mode) Jacobi passes until nothing changes anywhere, or
-        `iters` passes; returns [(edges, changed)] with global counts"""
+    def refine(self, dist_mat, T_grad, iters=-1, mode='all'):
+        """thread_handlers.refine (thread_handlers.py:128-236) across the slabs; returns
+        [(edges, changed)] with global counts, like the single-GPU history.
+
+        'all': a fresh edge pass before every Jacobi trace, until nothing changes anywhere or
+        `iters` passes.  'changed': after the first pass only the neighbourhoods of the
+        voxels that changed are re-classified (refinement.edge_check) -- the centre selection
+        of that function follows the global scan order, so the ranks iterate it together,
+        exchanging the halo planes of the known array until no voxel is undecided."""
         be, dev = self.backend, self.backend.labels().device
+        changed_mode = mode.lower() != 'all' and hasattr(be, 'ec_begin')
         history = []
-        it = 0
+        if iters == 0:
+            return history
+        if self.native_loops:
+            self._phase('refine:native')
+            history = be.refine_native('changed' if changed_mode else 'all', iters, dist_mat, T_grad)
+            self._phase(None)
+            return history
         dbg = os.environ.get('BDR_DEBUG') and self.comm.rank == 0
+
+        def counts(*vals):
+            t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=dev)
+            if self.comm.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.comm.group)
+            return [int(v) for v in t.tolist()]
+
+        it = 0
+        edges = changed = 0
         while iters < 0 or it < iters:
             self._phase('refine:halo')
             self.exchange_halo(be.labels())
-            self._phase('refine:edge_pass')
-            edges = be.edge_pass()
-            # every rank's classification must be complete before any rank's
-            # trajectories may read it (remote reads in the trace kernel)
-            edges = self.comm.allreduce_sum(edges, dev)
+            if it == 0 or not changed_mode:
+                self._phase('refine:edge_pass')
+                # every rank's classification must be complete before any rank's
+                # trajectories may read it (remote reads in the trace kernel): the
+                # all-reduce of the edge count is that barrier
+                edges, = counts(be.edge_pass())
+                if edges == 0:
+                    break
+            else:
+                self._phase('refine:edge_check')
+                be.ec_begin()
+                for _ in range(1 << 20):
+                    self.exchange_halo(be.known())
+                    undecided, = counts(be.ec_round())
+                    if undecided == 0:
+                        break
+                self.exchange_halo(be.known())
+                edges, = counts(be.ec_finish())
             self._phase('refine:trace')
-            changed, escaped = be.trace_pass(dist_mat, T_grad)
+            ch, esc = be.trace_pass(dist_mat, T_grad, want_list=changed_mode)
             self._phase('refine:reduce')
-            if self.comm.allreduce_sum(escaped, dev):
+            changed, escaped = counts(ch, esc)
+            if escaped:
                 raise RuntimeError("a trajectory left the slab halo: raise `halo`")
-            changed = self.comm.allreduce_sum(changed, dev)
             history.append((edges, changed))
             if dbg:
                 print(f"[sharded] pass {it}: edges {edges} changed {changed}", file=sys.stderr, flush=True)
             it += 1
-            if changed == 0 or edges == 0:
+            if changed == 0:
+                if it == 1 and (iters < 0 or iters >= 2):
+                    # the reference runs its second iteration on the unchanged labels: a fresh
+                    # edge_find finds the same edges ('all'), edge_check nothing ('changed')
+                    history.append((0, 0) if changed_mode else (edges, 0))
                 break
         self._phase('refine:halo')
         self.exchange_halo(be.labels())
@@ -330,6 +390,14 @@ class ShardedBader:
             return self.maxima
         dev, H, P = be.labels().device, self.halo, self.plane
         lab = be.labels()
+        if self.native_loops:
+            self._phase('rounds:native')
+            hist, self.settled = be.rounds_native(dist_mat, T_grad, max_passes)
+            self._phase('rounds:number')
+            self.renumber()      # the LUT pass covers the whole window: halo labels stay consistent
+            self._phase(None)
+            self.neargrid_history = hist
+            return self.maxima
         self._phase('rounds:halo')
         self.exchange_halo(lab)
         self._phase('rounds:first_pass')
@@ -397,10 +465,15 @@ class SlabBackend:
         h = ctypes.c_void_p()
         check(self.lib.bdr_slab_create(int(device), *self.shape, int(halo), ctypes.byref(h)))
         self.h = h
+        # one stream for the library's kernels and torch's (NCCL-ordered) work on the window
+        # tensors: no device-wide synchronisation between a halo exchange and the next kernel
+        torch.cuda.set_device(self.device)
+        check(self.lib.bdr_set_stream(self.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.N = int(np.prod(self.shape))
         self.n_real = 0
         self.exit_base = 0
         self._labels = None
+        self._known = None
         self._roots = None
         self._keep = []
 
@@ -443,9 +516,9 @@ class SlabBackend:
                                                 tz.ctypes.data, tx.shape[0]))
 
     def _sync(self):
-        """torch works on its own stream, the library on the handle's: order them
-        (a late halo copy into the label array must not land on fresh codes)"""
-        torch.cuda.synchronize(self.device)
+        """the library runs on torch's current stream (bdr_set_stream): torch's copies into
+        the window tensors and the library's kernels are ordered by the stream itself"""
+        return
 
     def clear_labels(self):
         self._sync()
@@ -490,7 +563,6 @@ class SlabBackend:
 
     def apply_rank(self, rank_lut):
         rank_lut = rank_lut.contiguous()
-        torch.cuda.synchronize(self.device)
         self.check(self.lib.bdr_slab_apply_rank(self.h, rank_lut.data_ptr()))
 
     def first_voxel_labels(self, n_labels):
@@ -504,8 +576,54 @@ class SlabBackend:
         self._sync()
         self.check(self.lib.bdr_slab_relabel(self.h, 0, lut.data_ptr()))
 
+    def comm_id(self):
+        buf = ctypes.create_string_buffer(128)
+        self.check(self.lib.bdr_slab_comm_id(buf))
+        return buf.raw
+
+    def comm_init(self, world, rank, ident):
+        self.check(self.lib.bdr_slab_comm_init(self.h, int(world), int(rank), ident))
+
+    def exchange(self, what):
+        self.check(self.lib.bdr_slab_exchange(self.h, int(what)))
+
+    def rounds_native(self, dist_mat, T_grad, max_passes=64, cap=256):
+        d = np.ascontiguousarray(dist_mat, dtype=np.float64)
+        t = np.ascontiguousarray(T_grad, dtype=np.float64)
+        hist = np.zeros((cap, 2), dtype=np.int64)
+        n, settled = ctypes.c_int64(0), ctypes.c_int(0)
+        self.check(self.lib.bdr_slab_rounds(self.h, 0, d.ctypes.data, t.ctypes.data, int(max_passes),
+                                            hist.ctypes.data, cap, ctypes.byref(n), ctypes.byref(settled)))
+        return [tuple(int(x) for x in r) for r in hist[:min(n.value, cap)]], bool(settled.value)
+
+    def refine_native(self, mode, iters, dist_mat, T_grad, cap=256):
+        d = np.ascontiguousarray(dist_mat, dtype=np.float64)
+        t = np.ascontiguousarray(T_grad, dtype=np.float64)
+        hist = np.zeros((cap, 2), dtype=np.int64)
+        n = ctypes.c_int64(0)
+        self.check(self.lib.bdr_slab_refine(self.h, 0, 0 if mode == 'all' else 1, int(iters), d.ctypes.data,
+                                            t.ctypes.data, ctypes.byref(n), hist.ctypes.data, cap))
+        return [tuple(int(x) for x in r) for r in hist[:min(n.value, cap)]]
+
+    def known(self):
+        if self._known is None:
+            self._known = torch.as_tensor(_DevArray(self._ptr(5), self.shape, '|i1'), device=self.device)
+        return self._known
+
+    def ec_begin(self):
+        self.check(self.lib.bdr_slab_ec_begin(self.h, 0))
+
+    def ec_round(self):
+        u = ctypes.c_int64(0)
+        self.check(self.lib.bdr_slab_ec_round(self.h, ctypes.byref(u)))
+        return u.value
+
+    def ec_finish(self):
+        e = ctypes.c_int64(0)
+        self.check(self.lib.bdr_slab_ec_finish(self.h, 0, ctypes.byref(e)))
+        return e.value
+
     def edge_pass(self):
-        torch.cuda.synchronize(self.device)
         e = ctypes.c_int64(0)
         self.check(self.lib.bdr_edge_pass(self.h, 0, ctypes.byref(e)))
         return e.value
@@ -533,13 +651,12 @@ class SlabBackend:
                                              int(extra.numel()), ctypes.byref(q)))
         return q.value
 
-    def trace_pass(self, dist_mat, T_grad):
-        self._sync()
+    def trace_pass(self, dist_mat, T_grad, want_list=False):
         d = np.ascontiguousarray(dist_mat, dtype=np.float64)
         t = np.ascontiguousarray(T_grad, dtype=np.float64)
         ch, esc = ctypes.c_int64(0), ctypes.c_int64(0)
-        self.check(self.lib.bdr_trace_pass(self.h, 0, d.ctypes.data, t.ctypes.data,
-                                           ctypes.byref(ch), ctypes.byref(esc)))
+        self.check(self.lib.bdr_trace_pass_list(self.h, 0, d.ctypes.data, t.ctypes.data, int(want_list),
+                                                ctypes.byref(ch), ctypes.byref(esc)))
         return ch.value, esc.value
 
     def charge_sum(self, n, dV, which_density=0):
@@ -590,12 +707,13 @@ def bench(args, rank, world, local):
     def step():
         sb.backend.clear_labels()
         sb.neargrid(dm, T)                 # ongrid seed + exits + numbering + rounds to quiescence
-        return sb.refine(dm, T, 2)         # the caller's refine(): full pass(es)
+        return sb.refine(dm, T, 2, mode='changed')   # the caller's refine(), same mode as one GPU
 
     be = sb.backend
     dev = torch.device('cuda', local)
     for _ in range(args.warmup):
         hist = step()
+    sb.phase_ms = {}
     clocks = B.ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -668,7 +786,7 @@ def bench(args, rank, world, local):
                       "bdr_download_labels(narrowed); max over ranks"}
         del host_rho, host_lab
     if rank == 0 and getattr(sb, 'phase_ms', None):
-        nst = args.warmup + args.steps * (1 if args.no_e2e else 2) + (0 if args.no_e2e else 1)
+        nst = args.steps * (1 if args.no_e2e else 2) + (0 if args.no_e2e else 1)
         print("[sharded] phases, ms per step (BDR_PHASES): " +
               ", ".join(f"{k} {v / nst:.2f}" for k, v in sb.phase_ms.items()), file=sys.stderr)
     if rank == 0:
@@ -679,9 +797,9 @@ def bench(args, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": B.workload_name(shape, "('all',2)"), "atoms": len(case['amps']),
+            "config": {"workload": B.workload_name(shape), "atoms": len(case['amps']),
                        "maxima": int(sb.maxima.shape[0]), "method": "neargrid",
-                       "refine_method": "neargrid", "refine_mode": ["all", 2],
+                       "refine_method": "neargrid", "refine_mode": ["changed", 2],
                        "parallelism": f"{world} x-slabs, halo {args.halo} planes, NCCL ring exchange "
                                       f"of halo planes / exit labels, NVLink peer loads in the trace",
                        "l2": "per-GPU inputs are far larger than the 126 MB L2; no flush"},

@@ -99,7 +99,7 @@ class ModelBackend:
         orc.edge_find(self.known, self.rho, self.lab)
         return int((self.known.reshape(-1)[self.own_lo:self.own_hi] == -2).sum())
 
-    def trace_pass(self, dist_mat, T_grad):
+    def trace_pass(self, dist_mat, T_grad, want_list=False):
         before = self.lab.reshape(-1)[self.own_lo:self.own_hi].copy()
         orc.refine_neargrid(self.known, self.known.copy(), self.rho, self.lab, dist_mat, T_grad)
         after = self.lab.reshape(-1)[self.own_lo:self.own_hi]

@@ -21,8 +21,10 @@ def _free_port():
 
 
 CASES = {
-    # name: (world, shape, halo)
+    # name: (world, shape, halo); *_pyproto drives the round loops from Python
+    # (BDR_PY_PROTOCOL=1, the code path the gloo CPU tests cover) instead of from the library
     'w2_toy_halo8': (2, (96, 64, 80), 8),
+    'w2_toy_halo8_pyproto': (2, (96, 64, 80), 8),
     'w2_512_halo4': (2, (512, 256, 256), 4),      # the bench's halo
     'w4_512_halo4': (4, (512, 256, 256), 4),
     'w8_512_halo4': (8, (512, 256, 256), 4),
@@ -67,16 +69,23 @@ def _worker(rank, world, port, out, shape, halo):
         hist = sb.refine(dm, T, -1)
         lab_ng = sb.owned_labels().cpu().numpy().copy()
         q, v = sb.charge_sum(mx.shape[0], dV)
-        # bader_calc('neargrid') of the sharded path: incremental rounds, then one exact pass
+        # 'changed'-mode refinement across the slabs (edge_check's centre selection follows the
+        # global scan order): from the same ongrid labels
+        sb.backend.clear_labels()
+        sb.ongrid(dm)
+        hist_c = sb.refine(dm, T, 3, mode='changed')
+        lab_c = sb.owned_labels().cpu().numpy().copy()
+        # bader_calc('neargrid') of the sharded path: incremental rounds, then the caller's
+        # refine(('changed', 2)) like the bench step
         sb.backend.clear_labels()
         mx2 = sb.neargrid(dm, T)
         assert sb.settled
-        hist2 = sb.refine(dm, T, 1)
+        hist2 = sb.refine(dm, T, 2, mode='changed')
         lab_nn = sb.owned_labels().cpu().numpy().copy()
         q2, v2 = sb.charge_sum(mx2.shape[0], dV)
         np.savez(os.path.join(out, f'r{rank}.npz'), maxima=mx, lab_on=lab_on, lab_ng=lab_ng,
                  hist=np.array(hist), q=q, v=v, maxima2=mx2, lab_nn=lab_nn, hist2=np.array(hist2),
-                 q2=q2, v2=v2)
+                 q2=q2, v2=v2, lab_c=lab_c, hist_c=np.array(hist_c))
     finally:
         dist.destroy_process_group()
 
@@ -90,7 +99,14 @@ def test_sharded_labels_equal_single_gpu(tmp_path, name):
         pytest.skip(f"needs {world} GPUs")
     from pybader_b200 import build
     build.build()
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shape, halo), nprocs=world, join=True)
+    if name.endswith('_pyproto'):
+        os.environ['BDR_PY_PROTOCOL'] = '1'
+    else:
+        os.environ.pop('BDR_PY_PROTOCOL', None)
+    try:
+        mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shape, halo), nprocs=world, join=True)
+    finally:
+        os.environ.pop('BDR_PY_PROTOCOL', None)
     from pybader_b200.engine import Engine, LABELS_BADER
     rho, dm, T, dV = _case(shape)
     e = Engine(rho.shape)
@@ -102,9 +118,12 @@ def test_sharded_labels_equal_single_gpu(tmp_path, name):
     ref_ng = e.download_labels(LABELS_BADER, np.int32)
     q, v = np.zeros(mx.shape[0]), np.zeros(mx.shape[0])
     e.charge_sum(LABELS_BADER, 0, dV, q, v)
+    e.upload_labels(LABELS_BADER, ref_on)
+    hist_c = e.refine(LABELS_BADER, 'changed', 3, dm, T)
+    ref_c = e.download_labels(LABELS_BADER, np.int32)
     e.clear_labels()
     mxn = e.bader_calc('neargrid', dm, T)
-    e.refine(LABELS_BADER, 'all', 1, dm, T)
+    hist_n = e.refine(LABELS_BADER, 'changed', 2, dm, T)
     ref_nn = e.download_labels(LABELS_BADER, np.int32)
     qn, vn = np.zeros(mxn.shape[0]), np.zeros(mxn.shape[0])
     e.charge_sum(LABELS_BADER, 0, dV, qn, vn)
@@ -116,14 +135,17 @@ def test_sharded_labels_equal_single_gpu(tmp_path, name):
     assert [tuple(h) for h in parts[0]['hist']] == hist
     np.testing.assert_allclose(parts[0]['q'], q, rtol=1e-12)
     np.testing.assert_allclose(parts[0]['v'], v, rtol=1e-12)
+    np.testing.assert_array_equal(np.concatenate([p['lab_c'] for p in parts]), ref_c)
+    assert [tuple(h) for h in parts[0]['hist_c']] == hist_c, (parts[0]['hist_c'], hist_c)
     # sharded bader_calc('neargrid') + one exact pass vs the single-GPU one: same
     # maxima, the exact pass finds (next to) nothing to do, labels >= 99.9 % equal
     np.testing.assert_array_equal(parts[0]['maxima2'], mxn)
     assert int(parts[0]['hist2'][0][1]) <= max(2, 1e-4 * ref_nn.size)
     lab_nn = np.concatenate([p['lab_nn'] for p in parts])
     assert np.mean(lab_nn == ref_nn) >= 0.999
-    print(f"{name}: ongrid and ongrid+refine(all,-1) labels bit-identical to 1 GPU over {world} ranks "
-          f"({len(hist)} passes); neargrid: {int(np.count_nonzero(lab_nn != ref_nn))} of {ref_nn.size} "
-          f"voxels differ")
+    print(f"{name}: ongrid, ongrid+refine(all,-1) ({len(hist)} passes) and ongrid+refine(changed,3) "
+          f"(history {hist_c}) labels bit-identical to 1 GPU over {world} ranks; neargrid+refine(changed,2): "
+          f"{int(np.count_nonzero(lab_nn != ref_nn))} of {ref_nn.size} voxels differ, history "
+          f"{[tuple(h) for h in parts[0]['hist2']]} vs {hist_n} on 1 GPU")
     np.testing.assert_allclose(parts[0]['q2'], qn, rtol=1e-6)
     np.testing.assert_allclose(parts[0]['v2'], vn, rtol=1e-6)
