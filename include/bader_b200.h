@@ -55,7 +55,8 @@ enum {
     BDR_K_SYNTH = 12,      /* synthetic density generator             */
     BDR_K_FIRST = 13,      /* first-voxel (numbering) pass            */
     BDR_K_EDGE_CONFIRM = 14, /* edge candidates -> edges (density test) */
-    BDR_K_COUNT = 15
+    BDR_K_TRACE_PEER = 15, /* sharded runs: walks continued on other ranks' memory */
+    BDR_K_COUNT = 16
 };
 
 const char *bdr_last_error(void);

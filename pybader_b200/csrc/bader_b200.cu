@@ -486,7 +486,8 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
         TRY(ensure(&c->defer, &c->defer_cap, nd));  // redo the pass with room for every deferred voxel
     }
     c->list_n = n;  // every candidate of the window; the trace kernel skips what it does not own
-    c->window_fresh = n_changed < 0 && sticky_mode == 0;
+    c->window_fresh = n_changed < 0;   // a full pass over the whole window (exact or conservative)
+    c->halo_known_current = false;
     *edges = 0;
     if (n == 0) return 0;
     if (sticky_mode != 0) {
@@ -562,6 +563,7 @@ static int incremental_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *qu
     *queued = 0;
     c->list_n = 0;
     c->window_fresh = false;
+    c->halo_known_current = false;
     if (n_changed == 0) return 0;
     const int64_t cap = std::min<int64_t>(n_changed * 27, c->N);
     TRY(ensure(&c->list3, &c->list3_cap, cap));
@@ -637,16 +639,24 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
         // an exact pass follows a full edge pass over the whole window on freshly exchanged
         // labels: the classification of planes [2, W-3] equals the owners', and the labels read
         // there belong to interior voxels or maxima, which no rank writes during the pass
-        if (c->window_fresh && !c->use_term) {
+        // (the conservative first pass of bader_calc('neargrid') qualifies as well: trajectory
+        // ends off the owned planes are simply not cached, see k_trace)
+        if (c->window_fresh) {
             win.xlo = 2;
             win.xhi = c->g.nx - 3;
+        }
+        // the library's own round loops copy the owners' known planes into the halos after
+        // every classification step: every plane whose stencil fits the window is trusted
+        if (c->halo_known_current) {
+            win.xlo = 1;
+            win.xhi = c->g.nx - 2;
         }
     }
     if (!pv || local_first) {
         LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
                rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, win, W, T, c->list, n,
                chunk, (int32_t *)nullptr, c->d_cnt, chg, c->list2_cap, c->list3, c->list3_cap, step_cap,
-               term, local_first ? 1 : 0);
+               term, local_first ? 1 : 0, c->halo_known_current ? 1 : 0);
         TRY(read_counters(c));
         if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
     }
@@ -662,7 +672,7 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
                 LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
                        rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
                        W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt, chg, c->list2_cap,
-                       (int32_t *)nullptr, (int64_t)0, step_cap, term, 0);
+                       (int32_t *)nullptr, (int64_t)0, step_cap, term, 0, 0);
             }
             TRY(read_counters(c));
             if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
@@ -680,7 +690,13 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
             TRY(ensure(&c->list4, &c->list4_cap, m_in));
             CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
             const int pchunk = local_first ? 32 : chunk;
-            LAUNCH(c, BDR_K_TRACE, (k_trace_peer<PATH_FAST, false>),
+            PeerView pvl = *pv;   // what the local kernel trusted is read locally here as well
+            pvl.tlo = local_first ? win.xlo : c->halo;
+            pvl.thi = local_first ? win.xhi : c->g.nx - c->halo - 1;
+            pvl.clo = c->halo_known_current ? pvl.tlo : c->halo;
+            pvl.chi = c->halo_known_current ? pvl.thi : c->g.nx - c->halo - 1;
+            pv = &pvl;
+            LAUNCH(c, BDR_K_TRACE_PEER, (k_trace_peer<PATH_FAST, false>),
                    blocks_for((m_in + pchunk - 1) / pchunk * 32, 128), 128, 0, *pv, c->labels[which],
                    c->known, c->g, window_of(c), W, T, in, m_in, pchunk, (long long *)nullptr, c->d_cnt,
                    chg, c->list2_cap, c->list4, c->list4_cap, step_cap, term);
@@ -692,7 +708,7 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
                 CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
                 for (int64_t o = 0; o < ov; o += batch) {
                     const int64_t m = std::min(batch, ov - o);
-                    LAUNCH(c, BDR_K_TRACE, (k_trace_peer<SLOW_CAP, true>), blocks_for(m, 128), 128, 0, *pv,
+                    LAUNCH(c, BDR_K_TRACE_PEER, (k_trace_peer<SLOW_CAP, true>), blocks_for(m, 128), 128, 0, *pv,
                            c->labels[which], c->known, c->g, window_of(c), W, T, c->list4 + o, m, 32,
                            (long long *)c->stage, c->d_cnt, chg, c->list2_cap, (int32_t *)nullptr,
                            (int64_t)0, step_cap, term);
@@ -738,6 +754,7 @@ static int ec_finish_dev(bdr_ctx *c, int which, int64_t n_changed, int64_t *edge
     *edges = 0;
     c->list_n = 0;
     c->window_fresh = false;   // only the neighbourhoods of the centres were re-classified
+    c->halo_known_current = false;
     const double *rho = rho_ptr(c, BDR_RHO_REFERENCE);
     const int32_t *lab = c->labels[which];
     const int64_t plane = (int64_t)c->g.ny * c->g.nz;
@@ -1316,6 +1333,16 @@ int bdr_slab_exchange(bdr_ctx *c, int what) {
     return fail_msg("bdr_slab_exchange: bad selector");
 }
 
+// every rank's classification of its own planes goes to the neighbours' halos: walks that
+// leave the slab by less than `halo` planes then run on local copies of exactly the bytes
+// the owner holds, and only deeper ones take the peer kernel's remote loads
+static int slab_publish_known(bdr_ctx *c, SlabComm *sc) {
+    if (getenv("BDR_NO_KNOWN_EXCHANGE")) return 0;
+    TRY(comm_halo_exchange(c, sc, c->known, 1));
+    c->halo_known_current = true;
+    return 0;
+}
+
 // bader_calc('neargrid') of a sharded run after the seed is numbered: the conservative
 // rounds of converge_rounds, the ranks meeting at one all-reduce per decision
 int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
@@ -1342,6 +1369,7 @@ int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double 
     TRY(comm_halo_exchange(c, sc, lab, 4));
     int64_t e = 0;
     TRY(edge_find_dev(c, which, &e, -1, 1));
+    TRY(slab_publish_known(c, sc));
     c->last_changed = 0;
     if (!c->term) CU(cudaMalloc((void **)&c->term, (size_t)c->N * sizeof(int32_t)));
     CU(cudaMemsetAsync(c->term, 0xff, (size_t)c->N * sizeof(int32_t), c->stream));
@@ -1393,6 +1421,7 @@ int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double 
         } else {
             TRY(incremental_dev(c, which, n, &q));
         }
+        TRY(slab_publish_known(c, sc));
         TRY(filter_cached_dev(c));
         v[0] = c->list_n;
         TRY(comm_allreduce(c, sc, 1, v));
@@ -1447,6 +1476,7 @@ int bdr_slab_refine(bdr_ctx *c, int which, int mode, int64_t iters, const double
         if (it == 0 || !chg_mode) {
             int64_t e = 0;
             TRY(edge_find_dev(c, which, &e));
+            TRY(slab_publish_known(c, sc));
             v[0] = e;
             TRY(comm_allreduce(c, sc, 1, v));      // the barrier before the remote reads, too
             edges = v[0];
@@ -1465,6 +1495,7 @@ int bdr_slab_refine(bdr_ctx *c, int which, int mode, int64_t iters, const double
             TRY(comm_halo_exchange(c, sc, c->known, 1));
             int64_t e = 0;
             TRY(ec_finish_dev(c, which, c->last_changed, &e));
+            TRY(slab_publish_known(c, sc));
             v[0] = e;
             TRY(comm_allreduce(c, sc, 1, v));
             edges = v[0];

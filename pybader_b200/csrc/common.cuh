@@ -109,6 +109,7 @@ struct bdr_ctx {
     int64_t N = 0;
     int halo = 0;               // slab windows: extra x planes on each side (0 = periodic grid)
     int64_t own_lo = 0, own_hi = 0;  // owned linear index range
+    bool halo_known_current = false;  // the halo planes of known are copies of the owners' planes (native slab loops)
     bool window_fresh = false;  // known holds a full exact classification of the whole window (slab passes)
     int64_t escaped = 0;        // trajectories that left the trusted planes in the last trace
 

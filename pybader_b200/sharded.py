@@ -743,6 +743,9 @@ def bench(args, rank, world, local):
     clock_info = clocks.stop() if rank == 0 else None
     ms = comm.allreduce_max(ms, dev)
     launches = comm.allreduce_sum(launches, dev)
+    ksum = sum(v[0] for v in prof.values()) / args.steps
+    ksum_max = comm.allreduce_max(ksum, dev)           # slowest rank's kernels: the load imbalance
+    ktrace_max = comm.allreduce_max(prof.get('trace', (0.0, 0))[0] / args.steps, dev)
     ms_per_step = ms / args.steps
 
     # ---- e2e: every rank uploads its slab window from pinned host memory, runs the
@@ -807,6 +810,7 @@ def bench(args, rank, world, local):
             "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
             "wall_ms_per_step": wall / args.steps, "kernels": kernels,
             "refine_history_last_step": hist,
+            "kernel_ms_per_step": {"rank0": ksum, "max_over_ranks": ksum_max, "trace_max_over_ranks": ktrace_max},
             "exit_rounds": sb.exit_rounds, "neargrid_passes": len(sb.neargrid_history),
             "neargrid_settled": sb.settled,
         }
