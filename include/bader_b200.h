@@ -262,6 +262,14 @@ int bdr_slab_trace(bdr_ctx *ctx, int which, const double *dist_mat, const double
 int bdr_slab_requeue(bdr_ctx *ctx, int which, const int32_t *dev_extra, int64_t n_extra,
                      int64_t *queued);
 
+/* One rank's share of thread_handlers.surface_distance (thread_handlers.py:239-297): exact
+ * edge pass on label set `which` of the window (halo labels must be current), then per atom
+ * the smallest SQUARED distance to an owned edge voxel of its volume (voxel positions are
+ * global), seen[a] != 0 iff the rank owns such a voxel, and the number of owned edges.  The
+ * caller reduces: min over ranks, sqrt; no edge anywhere -> the reference returns None.     */
+int bdr_slab_surface_distance(bdr_ctx *ctx, int which, const double *lattice, const double *atoms_cart,
+                              int64_t n_atoms, double *best_sq, int64_t *seen, int64_t *edges_owned);
+
 /* Trajectories that leave a rank's window continue on the owning rank's memory
  * (CUDA IPC mappings over NVLink / NVSwitch) instead of needing deep halos:
  * export writes three 64-byte IPC handles (density, labels, known); attach

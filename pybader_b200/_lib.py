@@ -62,6 +62,7 @@ SIGNATURES = {
     "bdr_slab_first_pass": ([_p, _int, ctypes.POINTER(_i64)], _int),
     "bdr_slab_trace": ([_p, _int, _p, _p, _int, ctypes.POINTER(_i64)], _int),
     "bdr_slab_requeue": ([_p, _int, _p, _i64, ctypes.POINTER(_i64)], _int),
+    "bdr_slab_surface_distance": ([_p, _int, _p, _p, _i64, _p, _p, ctypes.POINTER(_i64)], _int),
     "bdr_slab_ipc_export": ([_p, _p], _int),
     "bdr_slab_ipc_attach": ([_p, _int, _int, _p, _p, _i64], _int),
     "bdr_edge_pass": ([_p, _int, ctypes.POINTER(_i64)], _int),

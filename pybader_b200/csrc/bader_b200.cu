@@ -1716,7 +1716,7 @@ int bdr_vacuum_assign(bdr_ctx *c, double vac_tol, double voxel_volume, int which
     TRY(zero_counter(c, CNT_VACUUM));
     const unsigned nb = std::min<unsigned>(blocks_for(c->N, 256 * 8), 148 * 16);
     LAUNCH(c, BDR_K_VACUUM, k_vacuum, nb, 256, 0, ref, dens, c->labels[BDR_LABELS_BADER], c->N,
-           vac_tol, c->d_sums, c->d_cnt + CNT_VACUUM);
+           vac_tol, c->d_sums, c->d_cnt + CNT_VACUUM, c->own_lo, c->own_hi);
     double s = 0;
     CU(cudaMemcpyAsync(&s, c->d_sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     TRY(read_counters(c));
@@ -1856,24 +1856,23 @@ int bdr_assign_atoms(bdr_ctx *c, const double *maxima_cart, int64_t n_max, const
     return 0;
 }
 
-int bdr_surface_distance(bdr_ctx *c, int which, const double *lattice, const double *atoms_cart,
-                         int64_t n_atoms, double *distance, int *found) {
-    TRY(check(c));
-    if (which < 0 || which > 1) return fail_msg("bdr_surface_distance: bad label set");
-    int64_t edges = 0;
-    TRY(edge_find_dev(c, which, &edges));
-    if (found) *found = edges > 0;
-    for (int64_t a = 0; a < n_atoms; ++a) distance[a] = 0.0;
-    if (edges == 0) return 0;
+// edge_find on label set `which`, then the smallest squared distance from every atom to an
+// (owned) edge voxel of its own volume over the 27 lattice images (utils.py:321-379)
+static int surface_distance_dev(bdr_ctx *c, int which, const double *lattice, const double *atoms_cart,
+                                int64_t n_atoms, std::vector<double> &best, std::vector<unsigned long long> &seen,
+                                int64_t *edges) {
+    TRY(edge_find_dev(c, which, edges));
+    // utils.py:341-343: the running minimum starts at nx^2+ny^2+nz^2
+    const PeerView *pv = static_cast<const PeerView *>(c->peer_view);
+    const int64_t NX = pv ? pv->NX : c->g.nx;
+    const double init = (double)(NX * NX + (int64_t)c->g.ny * c->g.ny + (int64_t)c->g.nz * c->g.nz);
+    best.assign((size_t)n_atoms, init);
+    seen.assign((size_t)n_atoms, 0);
+    if (c->list_n == 0) return 0;
     TRY(ensure_sums(c, 5 * n_atoms + 9));
     double *d_atoms = c->d_sums, *d_lat = d_atoms + 3 * n_atoms;
     unsigned long long *d_best = reinterpret_cast<unsigned long long *>(d_lat + 9);
     unsigned long long *d_seen = d_best + n_atoms;
-    // utils.py:341-343: the running minimum starts at nx^2+ny^2+nz^2
-    const double init = (double)((int64_t)c->g.nx * c->g.nx + (int64_t)c->g.ny * c->g.ny +
-                                 (int64_t)c->g.nz * c->g.nz);
-    std::vector<double> best((size_t)n_atoms, init);
-    std::vector<unsigned long long> seen((size_t)n_atoms, 0);
     CU(cudaMemcpyAsync(d_atoms, atoms_cart, (size_t)3 * n_atoms * sizeof(double),
                        cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_lat, lattice, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1881,15 +1880,49 @@ int bdr_surface_distance(bdr_ctx *c, int which, const double *lattice, const dou
                        c->stream));
     CU(cudaMemsetAsync(d_seen, 0, (size_t)n_atoms * sizeof(unsigned long long), c->stream));
     LAUNCH(c, BDR_K_SURFACE, k_surface_dist, blocks_for(c->list_n, 128), 128, 0, c->labels[which],
-           c->known, c->g, c->list, c->list_n, d_lat, d_atoms, d_best, d_seen, (int)n_atoms);
+           c->known, c->g, c->list, c->list_n, d_lat, d_atoms, d_best, d_seen, (int)n_atoms,
+           (int)c->own_lo, (int)c->own_hi, pv ? pv->x0w : 0, (int)NX);
     CU(cudaMemcpyAsync(best.data(), d_best, (size_t)n_atoms * sizeof(double), cudaMemcpyDeviceToHost,
                        c->stream));
     CU(cudaMemcpyAsync(seen.data(), d_seen, (size_t)n_atoms * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bdr_surface_distance(bdr_ctx *c, int which, const double *lattice, const double *atoms_cart,
+                         int64_t n_atoms, double *distance, int *found) {
+    TRY(check(c));
+    if (which < 0 || which > 1) return fail_msg("bdr_surface_distance: bad label set");
+    if (c->halo > 0) return fail_msg("bdr_surface_distance: slab windows go through bdr_slab_surface_distance");
+    int64_t edges = 0;
+    std::vector<double> best;
+    std::vector<unsigned long long> seen;
+    TRY(surface_distance_dev(c, which, lattice, atoms_cart, n_atoms, best, seen, &edges));
+    if (found) *found = edges > 0;
     // atoms that own no edge voxel keep 0 (thread_handlers.py:289-297)
     for (int64_t a = 0; a < n_atoms; ++a)
-        distance[a] = seen[(size_t)a] ? std::sqrt(best[(size_t)a]) : 0.0;
+        distance[a] = (edges > 0 && seen[(size_t)a]) ? std::sqrt(best[(size_t)a]) : 0.0;
+    return 0;
+}
+
+// one rank's share of thread_handlers.surface_distance: the smallest SQUARED distance per
+// atom over the edge voxels this slab owns (the caller takes the minimum over the ranks and
+// the square root), whether the atom's volume has an owned edge voxel, and the owned edges
+int bdr_slab_surface_distance(bdr_ctx *c, int which, const double *lattice, const double *atoms_cart,
+                              int64_t n_atoms, double *best_sq, int64_t *seen_out, int64_t *edges_owned) {
+    TRY(check(c));
+    if (which < 0 || which > 1) return fail_msg("bdr_slab_surface_distance: bad label set");
+    if (c->halo == 0) return fail_msg("bdr_slab_surface_distance: not a slab handle");
+    int64_t edges = 0;
+    std::vector<double> best;
+    std::vector<unsigned long long> seen;
+    TRY(surface_distance_dev(c, which, lattice, atoms_cart, n_atoms, best, seen, &edges));
+    for (int64_t a = 0; a < n_atoms; ++a) {
+        best_sq[a] = best[(size_t)a];
+        seen_out[a] = (int64_t)seen[(size_t)a];
+    }
+    if (edges_owned) *edges_owned = edges;
     return 0;
 }
 

@@ -7,16 +7,20 @@ C ABI instead of the numba jits.
     refine            thread_handlers.py:128-236
     surface_distance  thread_handlers.py:239-297
 
-`threads` is accepted and ignored (there is no CPU threading here).
+`threads` is accepted and ignored (there is no CPU threading here).  Under `torchrun`
+(WORLD_SIZE > 1) every entry point runs sharded over the ranks' GPUs
+(pybader_b200.sharded_handlers) and returns the same arrays on every rank.
 """
 import numpy as np
 
-from . import session
+from . import session, sharded_handlers
 from .engine import LABELS_ATOMS, LABELS_BADER, METHODS, MODES, REFINE_METHODS
 from .utils import dtype_calc
 
 
 def bader_calc(method, density, volumes, dist_mat, T_grad, threads=1):
+    if sharded_handlers.active():       # WORLD_SIZE > 1: x-slabs over the ranks' GPUs
+        return sharded_handlers.bader_calc(method, density, volumes, dist_mat, T_grad, threads)
     if method not in METHODS:
         # the reference does getattr(methods, method) (thread_handlers.py:26)
         raise AttributeError(f"module 'pybader.methods' has no attribute '{method}'")
@@ -29,6 +33,10 @@ def bader_calc(method, density, volumes, dist_mat, T_grad, threads=1):
 
 
 def refine(method, refine_mode, density, volumes, dist_mat, T_grad, threads=1):
+    if sharded_handlers.active():
+        sharded_handlers.refine(method, refine_mode, density, volumes, dist_mat, T_grad, threads)
+        refine.last_history = sharded_handlers.refine.last_history
+        return
     if method not in REFINE_METHODS:
         return  # getattr(refinement, method) fails -> silently no refinement (l.140-143)
     check_mode, iters = tuple(refine_mode)
@@ -48,6 +56,8 @@ refine.last_history = []
 
 
 def assign_to_atoms(bader_max, atoms, lattice, volumes, threads=1):
+    if sharded_handlers.active():
+        return sharded_handlers.assign_to_atoms(bader_max, atoms, lattice, volumes, threads)
     s = session.get(volumes.shape)
     s.label_slot(volumes, force=LABELS_BADER)
     bader_atoms, bader_distance = s.engine.assign_atoms(bader_max, atoms, lattice)
@@ -56,6 +66,8 @@ def assign_to_atoms(bader_max, atoms, lattice, volumes, threads=1):
 
 
 def surface_distance(density, volumes, lattice, atoms, threads=1):
+    if sharded_handlers.active():
+        return sharded_handlers.surface_distance(density, volumes, lattice, atoms, threads)
     s = session.get(density.shape)
     s.reference(density)
     slot = s.label_slot(volumes, prefer=LABELS_ATOMS)

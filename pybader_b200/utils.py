@@ -9,7 +9,7 @@
 """
 import numpy as np
 
-from . import session
+from . import session, sharded_handlers
 from .engine import LABELS_BADER, RHO_CHARGE, Engine
 
 
@@ -30,6 +30,8 @@ def dtype_calc(max_val):
 
 
 def vacuum_assign(reference, volumes, vac_tol, density, voxel_volume):
+    if sharded_handlers.active():
+        return sharded_handlers.vacuum_assign(reference, volumes, vac_tol, density, voxel_volume)
     s = session.get(reference.shape)
     s.reference(reference)
     dslot = s.density_slot(density, prefer=RHO_CHARGE)
@@ -44,6 +46,8 @@ def vacuum_assign(reference, volumes, vac_tol, density, voxel_volume):
 
 
 def charge_sum(charge, volume, voxel_volume, density, volumes):
+    if sharded_handlers.active():
+        return sharded_handlers.charge_sum(charge, volume, voxel_volume, density, volumes)
     s = session.get(volumes.shape)
     lslot = s.label_slot(volumes, prefer=LABELS_BADER)
     # first free slot: reference, then charge, then spin (so charge and spin
@@ -62,6 +66,8 @@ def atom_assign(bader_max, atoms, lattice, i_c=None):
 
 
 def volume_mask(volumes, density, vol_num):
+    if sharded_handlers.active():
+        return sharded_handlers.volume_mask(volumes, density, vol_num)
     s = session.get(volumes.shape)
     lslot = s.label_slot(volumes, prefer=LABELS_BADER)
     dslot = s.density_slot(density, prefer=s.free_density_slot())

@@ -131,3 +131,32 @@ def test_session_fingerprint_detects_change():
         assert _lib.load().bdr_host_hash(big.ctypes.data, big.nbytes, nt, ctypes.byref(h), ctypes.byref(z)) == 0
         hs.append(h.value)
     assert len(set(hs)) == 1
+
+
+def test_handlers_dispatch_to_the_sharded_engine_under_torchrun(monkeypatch):
+    """WORLD_SIZE > 1 (a torchrun launch) routes every reference-shaped entry point to
+    pybader_b200.sharded_handlers; WORLD_SIZE 1 keeps the single-GPU session"""
+    from pybader_b200 import sharded_handlers as sh, thread_handlers as th, utils as ut
+    monkeypatch.delenv('WORLD_SIZE', raising=False)
+    assert not sh.active()
+    monkeypatch.setenv('WORLD_SIZE', '1')
+    assert not sh.active()
+    monkeypatch.setenv('WORLD_SIZE', '4')
+    assert sh.active()
+    calls = []
+    for name in ('bader_calc', 'refine', 'assign_to_atoms', 'surface_distance', 'vacuum_assign',
+                 'charge_sum', 'volume_mask'):
+        monkeypatch.setattr(sh, name, (lambda n: (lambda *a, **k: calls.append(n) or n))(name))
+    sh.refine.last_history = []
+    a = np.zeros((2, 2, 2))
+    assert th.bader_calc('ongrid', a, a, a, a, 1) == 'bader_calc'
+    th.refine('neargrid', ('all', 1), a, a, a, a, 1)
+    assert th.assign_to_atoms(a, a, a, a, 1) == 'assign_to_atoms'
+    assert th.surface_distance(a, a, a, a, 1) == 'surface_distance'
+    assert ut.vacuum_assign(a, a, 0.0, a, 1.0) == 'vacuum_assign'
+    assert ut.charge_sum(a, a, 1.0, a, a) == 'charge_sum'
+    assert ut.volume_mask(a, a, 0) == 'volume_mask'
+    assert calls == ['bader_calc', 'refine', 'assign_to_atoms', 'surface_distance', 'vacuum_assign',
+                     'charge_sum', 'volume_mask']
+    monkeypatch.setenv('BDR_FORCE_SINGLE', '1')
+    assert not sh.active()
