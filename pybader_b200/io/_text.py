@@ -58,7 +58,13 @@ def parse_block(text, shape, x_fastest, op=OP_NONE, operand=1.0, device=0):
         nx, ny, nz = (int(s) for s in shape)
         flat = out.reshape(-1)
         for t, off, ln in fb[:nfb.value]:
-            v = float(bytes(buf[off:off + ln]))
+            # the device reports at most 64 bytes of a token: the whole whitespace-delimited
+            # token decides, as in the reference (a long valid number converts in full, junk
+            # behind the 64th byte still raises)
+            end = int(off + ln)
+            while end < buf.size and buf[end] not in (32, 10, 9, 13, 12, 11):
+                end += 1
+            v = float(bytes(buf[off:end]))
             if op == OP_DIVIDE:
                 v = v / operand
             elif op == OP_MULTIPLY:

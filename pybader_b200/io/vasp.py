@@ -90,16 +90,22 @@ def read(fn, charge_flag=True, spin_flag=False, buffer_size=64, device=0):
         if spin_flag:
             # the spin block follows the augmentation occupancies, behind a second
             # copy of the grid line (io/vasp.py:106-123 looks for it from mid-file)
-            f.seek(charge_end if charge_end is not None else charge_pos + est - line_len)
+            # The first piece of the tail is the rest of a line in both cases -- what is left
+            # of the last charge line, or (spin only) a line inside the charge block three
+            # lines before its estimated end, so that a grid line that starts exactly at the
+            # estimate (no augmentation block, grid_pts a multiple of the values per line) is
+            # a whole line of the tail and not mistaken for a partial one.
+            f.seek(charge_end if charge_end is not None
+                   else max(charge_pos, charge_pos + est - 4 * line_len))
             rest_pos = f.tell()
             tail = f.read()
             key = grid_line.strip()
-            hit, at = -1, 0
-            while True:
+            hit, at = -1, tail.find(b'\n') + 1
+            while at > 0:
                 nl = tail.find(b'\n', at)
                 if nl < 0:
                     break
-                if tail[at:nl].strip() == key and at > 0:
+                if tail[at:nl].strip() == key:
                     hit = nl + 1
                     break
                 at = nl + 1

@@ -132,3 +132,43 @@ def test_parse_block_large_and_fallback(tmp_path):
         parse_block(text[:len(text) // 2], shape, False)
     with pytest.raises(ValueError):
         parse_block(text.replace(b'E+00', b'*+00', 1), shape, False)
+
+
+@pytest.mark.gpu
+def test_spin_only_read_without_augmentation_block(tmp_path, capsys):
+    """a CHG-style file (no augmentation occupancies) whose grid is a multiple of
+    the values per line: the second grid line starts exactly where the charge block is
+    estimated to end, and the spin-only read must still find it"""
+    from pybader_b200.io import vasp
+    rng = np.random.default_rng(3)
+    nx, ny, nz = 5, 4, 3
+    n = nx * ny * nz
+    path = os.path.join(str(tmp_path), 'CHG_spin')
+    with open(path, 'w') as f:
+        f.write("chg fixture\n   1.00000000000000\n")
+        f.write("     4.000000    0.000000    0.000000\n     0.000000    5.000000    0.000000\n"
+                "     0.000000    0.000000    6.000000\n")
+        f.write("   Si\n     1\nDirect\n  0.100000  0.200000  0.300000\n\n")
+        for b in range(2):
+            f.write(f"   {nx}   {ny}   {nz}\n")
+            vals = rng.normal(0, 5, n)
+            for i in range(0, n, 5):
+                f.write(''.join(' %17.11E' % v for v in vals[i:i + 5]) + '\n')
+    both, *_ = vasp.read(path, charge_flag=True, spin_flag=True)
+    only, _, _, info = vasp.read(path, charge_flag=False, spin_flag=True)
+    assert info['spin_flag'] and set(only) == {'spin'}
+    assert only['spin'].tobytes() == both['spin'].tobytes()
+    assert not np.array_equal(both['spin'], both['charge'])
+
+
+@pytest.mark.gpu
+def test_fallback_tokens_longer_than_64_bytes():
+    """the device hands back at most 64 bytes of a token; the whole token decides"""
+    from pybader_b200.io._text import parse_block
+    long_ok = '0.' + '123456789' * 8 + 'E+01'          # 78 characters, a valid number
+    text = f"1.5 {long_ok} -2.25 4.0\n".encode()
+    a, _ = parse_block(text, (1, 2, 2), False)
+    assert a.reshape(-1).tolist() == [1.5, float(long_ok), -2.25, 4.0]
+    junk = '1.' + '0' * 70 + 'x'
+    with pytest.raises(ValueError):
+        parse_block(f"1.5 {junk} -2.25 4.0\n".encode(), (1, 2, 2), False)
