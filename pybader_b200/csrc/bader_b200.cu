@@ -652,44 +652,62 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
             win.xhi = c->g.nx - 2;
         }
     }
+    // scratch of the SLOW variant: a path buffer in global memory, in batches so that it
+    // stays bounded (SLOW_CAP entries per walk)
+    auto slow_pass = [&](const int32_t *in, int64_t ov, int32_t *esc_list, int64_t esc_cap) -> int {
+        TRY(ensure_stage(c, (size_t)(std::min(ov, batch) + 128) * SLOW_CAP * sizeof(long long)));
+        for (int64_t o = 0; o < ov; o += batch) {
+            const int64_t m = std::min(batch, ov - o);
+            LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
+                   rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, win, W, T, in + o, m, 32,
+                   (int32_t *)c->stage, c->d_cnt, chg, c->list2_cap, (int32_t *)nullptr, (int64_t)0, step_cap,
+                   term, esc_list, esc_cap, c->halo_known_current ? 1 : 0);
+        }
+        TRY(read_counters(c));
+        if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
+        return 0;
+    };
+    TRY(zero_counter(c, CNT_ESCLIST));
     if (!pv || local_first) {
+        // walks that leave the trusted planes are listed for the peer kernel (slab windows),
+        // walks that outgrow the register-file path buffer for the SLOW variant
+        int32_t *esc_list = nullptr;
+        if (local_first) {
+            TRY(ensure(&c->list4, &c->list4_cap, n));
+            esc_list = c->list4;
+        }
         LAUNCH(c, BDR_K_TRACE, (k_trace<PATH_FAST, false>), blocks_for(n_warps * 32, 128), 128, 0,
                rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, win, W, T, c->list, n,
                chunk, (int32_t *)nullptr, c->d_cnt, chg, c->list2_cap, c->list3, c->list3_cap, step_cap,
-               term, local_first ? 1 : 0, c->halo_known_current ? 1 : 0);
+               term, esc_list, c->list4_cap, c->halo_known_current ? 1 : 0);
         TRY(read_counters(c));
         if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
-    }
-    if (!pv) {
         const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
         if (ov > 0) {
-            // long paths: redo those voxels with a path buffer in global memory,
-            // in batches so the scratch stays bounded (SLOW_CAP * 4 B per voxel)
-            TRY(ensure_stage(c, (size_t)(std::min(ov, batch) + 128) * SLOW_CAP * sizeof(long long)));
+            // long paths stay local as long as they stay on trusted planes
             CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
-            for (int64_t o = 0; o < ov; o += batch) {
-                const int64_t m = std::min(batch, ov - o);
-                LAUNCH(c, BDR_K_TRACE, (k_trace<SLOW_CAP, true>), blocks_for(m, 128), 128, 0,
-                       rho_ptr(c, BDR_RHO_REFERENCE), c->labels[which], c->known, c->g, window_of(c),
-                       W, T, c->list3 + o, m, 32, (int32_t *)c->stage, c->d_cnt, chg, c->list2_cap,
-                       (int32_t *)nullptr, (int64_t)0, step_cap, term, 0, 0);
-            }
-            TRY(read_counters(c));
-            if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory longer than 4096 voxels");
+            TRY(slow_pass(c->list3, ov, esc_list, c->list4_cap));
         }
-    } else {
+    }
+    if (pv) {
         // stage 2 (slab windows): the peer kernel continues on the neighbours' memory
         // (K4p) -- over the walks stage 1 handed back, or over the whole list
         const int32_t *in = c->list;
         int64_t m_in = n;
+        int32_t *pov = c->list4;            // over-long walks of the peer kernel
         if (local_first) {
-            in = c->list3;
-            m_in = (int64_t)c->h_cnt[CNT_OVERFLOW];
+            in = c->list4;
+            m_in = (int64_t)c->h_cnt[CNT_ESCLIST];
+            pov = c->list3;                 // free again: the local SLOW pass is done
+        } else {
+            TRY(ensure(&c->list4, &c->list4_cap, m_in));
+            pov = c->list4;
         }
         if (m_in > 0) {
-            TRY(ensure(&c->list4, &c->list4_cap, m_in));
+            const int64_t pov_cap = local_first ? c->list3_cap : c->list4_cap;
             CU(cudaMemsetAsync(c->d_cnt + CNT_OVERFLOW, 0, sizeof(unsigned long long) * 2, c->stream));
-            const int pchunk = local_first ? 32 : chunk;
+            // (the escape list of a big pass is long enough for lanes to refill from a chunk)
+            const int pchunk = local_first ? (m_in > (1 << 20) ? 128 : (m_in > (1 << 17) ? 64 : 32)) : chunk;
             PeerView pvl = *pv;   // what the local kernel trusted is read locally here as well
             pvl.tlo = local_first ? win.xlo : c->halo;
             pvl.thi = local_first ? win.xhi : c->g.nx - c->halo - 1;
@@ -699,7 +717,7 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
             LAUNCH(c, BDR_K_TRACE_PEER, (k_trace_peer<PATH_FAST, false>),
                    blocks_for((m_in + pchunk - 1) / pchunk * 32, 128), 128, 0, *pv, c->labels[which],
                    c->known, c->g, window_of(c), W, T, in, m_in, pchunk, (long long *)nullptr, c->d_cnt,
-                   chg, c->list2_cap, c->list4, c->list4_cap, step_cap, term);
+                   chg, c->list2_cap, pov, pov_cap, step_cap, term);
             TRY(read_counters(c));
             if (c->h_cnt[CNT_ERROR]) return fail_msg("trace: trajectory exceeded the step cap");
             const int64_t ov = (int64_t)c->h_cnt[CNT_OVERFLOW];
@@ -709,7 +727,7 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
                 for (int64_t o = 0; o < ov; o += batch) {
                     const int64_t m = std::min(batch, ov - o);
                     LAUNCH(c, BDR_K_TRACE_PEER, (k_trace_peer<SLOW_CAP, true>), blocks_for(m, 128), 128, 0, *pv,
-                           c->labels[which], c->known, c->g, window_of(c), W, T, c->list4 + o, m, 32,
+                           c->labels[which], c->known, c->g, window_of(c), W, T, pov + o, m, 32,
                            (long long *)c->stage, c->d_cnt, chg, c->list2_cap, (int32_t *)nullptr,
                            (int64_t)0, step_cap, term);
                 }
@@ -1343,6 +1361,21 @@ static int slab_publish_known(bdr_ctx *c, SlabComm *sc) {
     return 0;
 }
 
+// relabelled voxels of the last trace (c->list2) within 2*halo planes of either end of the
+// owned slab: zero on every rank means no halo copy anywhere went stale
+static int slab_zone_changed(bdr_ctx *c, int64_t n_changed, int64_t *count) {
+    *count = 0;
+    if (n_changed == 0) return 0;
+    const int64_t plane = (int64_t)c->g.ny * c->g.nz;
+    const int64_t zone = 2 * (int64_t)c->halo;
+    TRY(zero_counter(c, CNT_CENTRES));
+    LAUNCH(c, BDR_K_EDGE_CHECK, k_count_zone, blocks_for(n_changed, 256), 256, 0, c->list2, n_changed,
+           (c->halo + zone) * plane, (c->g.nx - c->halo - zone) * plane, c->d_cnt + CNT_CENTRES);
+    TRY(read_counters(c));
+    *count = (int64_t)c->h_cnt[CNT_CENTRES];
+    return 0;
+}
+
 // bader_calc('neargrid') of a sharded run after the seed is numbered: the conservative
 // rounds of converge_rounds, the ranks meeting at one all-reduce per decision
 int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double *T_grad,
@@ -1355,6 +1388,10 @@ int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double 
     const Weights W = make_weights(dist_mat);
     const TGrad T = make_tgrad(T_grad);
     const bool dbg = getenv("BDR_DEBUG") != nullptr && sc->rank == 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [&]() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    };
     int64_t run = 0;
     auto record = [&](int64_t a, int64_t b) {
         if (history && run < hist_cap) {
@@ -1377,18 +1414,27 @@ int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double 
     long long v[2] = {(long long)e, 0};
     TRY(comm_allreduce(c, sc, 1, v));     // also the barrier before the first remote reads
     const int64_t edges = v[0];
-    int64_t changed = 0;
+    int64_t changed = 0, zone_changed = 0;
     if (edges > 0) {
-        int64_t ch = 0;
+        int64_t ch = 0, zc = 0;
         TRY(trace_dev(c, which, W, T, &ch, true));
         c->last_changed = ch;
+        TRY(slab_zone_changed(c, ch, &zc));
         v[0] = ch;
-        TRY(comm_allreduce(c, sc, 1, v));
+        v[1] = zc;
+        TRY(comm_allreduce(c, sc, 2, v));
         changed = v[0];
+        zone_changed = v[1];
     }
     record(edges, changed);
-    if (dbg) fprintf(stderr, "[bdr slab] first pass: edges %lld changed %lld\n", (long long)edges, (long long)changed);
+    if (dbg) fprintf(stderr, "[bdr slab] first pass: edges %lld changed %lld, %lld walks left the window  (t = %.2f ms)\n", (long long)edges, (long long)changed, (long long)c->h_cnt[CNT_ESCLIST], ms_since());
     while (changed > 0 && run < max_passes) {
+        // No rank relabelled anything within 2*halo planes of a slab boundary: every halo copy
+        // (labels and known) is still what its owner holds, and the re-classification below
+        // stays 2*halo - 2 planes away from the halos.  Nothing to exchange this round.
+        const bool quiet_boundaries = zone_changed == 0 && !getenv("BDR_ALWAYS_EXCHANGE");
+        int64_t n_extra = 0;
+        if (!quiet_boundaries) {
         // the planes next to the owned slab, before and after the exchange: voxels a
         // neighbour relabelled there count as changed here too
         CU(cudaMemcpyAsync(sc->plane_lo, lab + (int64_t)(H - 1) * plane, (size_t)plane * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -1414,26 +1460,35 @@ int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double 
                sc->plane_hi, (int)plane, (int)((Wp - H) * plane), c->d_cnt + CNT_CENTRES, c->list2, c->last_changed,
                c->list2_cap);
         TRY(read_counters(c));
-        const int64_t n = c->last_changed + (int64_t)c->h_cnt[CNT_CENTRES];
+        n_extra = (int64_t)c->h_cnt[CNT_CENTRES];
+        }
+        const int64_t n = c->last_changed + n_extra;
         int64_t q = 0;
-        if (n * 2048 > c->N) {
+        const bool full_pass = n * 2048 > c->N;
+        if (full_pass) {
             TRY(edge_find_dev(c, which, &q, n, 2));
         } else {
             TRY(incremental_dev(c, which, n, &q));
         }
-        TRY(slab_publish_known(c, sc));
+        // (a full pass rewrites the halo planes of known from the window's own view, so it is
+        // published again; the list-based update stays away from the halos in a quiet round)
+        if (quiet_boundaries && !full_pass) c->halo_known_current = true;
+        else TRY(slab_publish_known(c, sc));
         TRY(filter_cached_dev(c));
         v[0] = c->list_n;
         TRY(comm_allreduce(c, sc, 1, v));
         const int64_t queued = v[0];
-        int64_t ch = 0;
+        int64_t ch = 0, zc = 0;
         TRY(trace_dev(c, which, W, T, &ch, true));
         c->last_changed = ch;
+        TRY(slab_zone_changed(c, ch, &zc));
         v[0] = ch;
-        TRY(comm_allreduce(c, sc, 1, v));
+        v[1] = zc;
+        TRY(comm_allreduce(c, sc, 2, v));
         changed = v[0];
+        zone_changed = v[1];
         record(queued, changed);
-        if (dbg) fprintf(stderr, "[bdr slab] round %lld: queued %lld changed %lld\n", (long long)run - 1, (long long)queued, (long long)changed);
+        if (dbg) fprintf(stderr, "[bdr slab] round %lld: queued %lld changed %lld  (t = %.2f ms)\n", (long long)run - 1, (long long)queued, (long long)changed, ms_since());
     }
     c->use_term = false;
     c->last_changed = 0;

@@ -89,6 +89,7 @@ enum {
     CNT_STEPS = 10,    // trajectory steps taken by the trace kernel (accounting)
     CNT_DEFER = 12,    // edge pass: voxels next to vacuum, classified from a list (edge.cuh)
     CNT_VACSEEN = 13,  // edge pass: nonzero when the label volume holds vacuum voxels
+    CNT_ESCLIST = 14,  // slab windows: walks that left the trusted planes, listed for the peer kernel
     CNT_NUM = 16
 };
 

@@ -202,13 +202,12 @@ class ShardedBader:
         if n_real:
             G[exit_base:] = self._gid_of_window_index(be.roots().to(torch.int64))
 
+        vac = torch.tensor(VACUUM, dtype=torch.int64, device=dev)
+
         def export(plane_index):
             c = codes[plane_index].reshape(-1).to(torch.int64)
-            out = torch.full_like(c, VACUUM)
-            s = -2 - c
-            sel = c <= -2
-            out[sel] = G[s[sel]]
-            return out
+            # (no boolean-mask indexing here: it would synchronise the host on every call)
+            return torch.where(c <= -2, G[(-2 - c).clamp_(min=0)], vac)
 
         # one round per slab boundary an ascent path crosses (paths are acyclic, so
         # this ends; a path winding along a boundary can need more than `world`)
@@ -220,8 +219,10 @@ class ShardedBader:
             self.comm.ring_exchange(up, down, lo, hi)
             G[:P] = lo
             G[P:2 * P] = hi
-            pending = int(((up == UNRESOLVED).sum() + (down == UNRESOLVED).sum()).item())
-            pending = self.comm.allreduce_sum(pending, dev)
+            pending = ((up == UNRESOLVED).sum() + (down == UNRESOLVED).sum()).reshape(1)
+            if self.comm.world > 1:
+                dist.all_reduce(pending, op=dist.ReduceOp.SUM, group=self.comm.group)
+            pending = int(pending.item())
             if os.environ.get('BDR_DEBUG') and self.comm.rank == 0:
                 print(f"[sharded] exit round {self.exit_rounds}: pending {pending}", file=sys.stderr,
                       flush=True)
