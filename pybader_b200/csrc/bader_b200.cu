@@ -1464,15 +1464,15 @@ int bdr_slab_rounds(bdr_ctx *c, int which, const double *dist_mat, const double 
         }
         const int64_t n = c->last_changed + n_extra;
         int64_t q = 0;
-        const bool full_pass = n * 2048 > c->N;
-        if (full_pass) {
+        // (a quiet round takes the list-based update whatever its size: that one stays away
+        // from the halo planes of known, which therefore remain the owners' copies -- and the
+        // choice between the two updates may differ from rank to rank, an exchange may not)
+        if (n * 2048 > c->N && !quiet_boundaries) {
             TRY(edge_find_dev(c, which, &q, n, 2));
         } else {
             TRY(incremental_dev(c, which, n, &q));
         }
-        // (a full pass rewrites the halo planes of known from the window's own view, so it is
-        // published again; the list-based update stays away from the halos in a quiet round)
-        if (quiet_boundaries && !full_pass) c->halo_known_current = true;
+        if (quiet_boundaries) c->halo_known_current = true;
         else TRY(slab_publish_known(c, sc));
         TRY(filter_cached_dev(c));
         v[0] = c->list_n;
