@@ -228,6 +228,22 @@ def reference_arm(args):
         rate = rho.size / (time.perf_counter() - t0)
         sp = args.ref_spacing or pick_spacing(rate * 1.5, total_steps, args.ref_budget)
         rho, dist, T = ref_sample_inputs(sp)
+        if not args.ref_spacing:
+            # the small cell under-estimates the rate of a large one: time one step of the chosen
+            # cell and move one notch up or down (at most three times) to fill the budget
+            ladder = [SPACING, 176.0, 160.0, 144.0, 128.0, 112.0, 96.0, 80.0, 64.0, 48.0]
+            for _ in range(3):
+                t0 = time.perf_counter()
+                numba_step(ref, rho, dist, T, cores)
+                t1 = time.perf_counter() - t0
+                i = ladder.index(sp)
+                if t1 * total_steps > 1.3 * args.ref_budget and i + 1 < len(ladder):
+                    sp = ladder[i + 1]
+                elif i > 0 and t1 * total_steps * (ladder[i - 1] / sp) ** 3 < 0.9 * args.ref_budget:
+                    sp = ladder[i - 1]
+                else:
+                    break
+                rho, dist, T = ref_sample_inputs(sp)
         n_vox = rho.size
 
         def one_step():

@@ -122,6 +122,38 @@ static int ensure_bits(bdr_ctx *c) {
     c->eqx = c->eqy + words;
     return 0;
 }
+// the label set's equality bits no longer describe it (labels rewritten wholesale)
+static void eq_invalidate(bdr_ctx *c, int which) {
+    if (which < 0 || c->eq_which == which) {
+        c->eq_valid = false;
+        c->eq_pending_n = 0;
+    }
+}
+// voxels a trace relabelled (c->list2[0, n)) join the list k_eq_update will patch in
+static int eq_note_changed(bdr_ctx *c, int which, int64_t n, bool have_list) {
+    if (!c->eq_valid || c->eq_which != which || n == 0) return 0;
+    if (!have_list || c->eq_pending_n + n > c->N / 32) {   // cheaper to recompute than to patch
+        eq_invalidate(c, which);
+        return 0;
+    }
+    if (c->eq_pending_n + n > c->eq_pending_cap) {
+        const int64_t cap = (c->eq_pending_n + n) * 2 + 4096;
+        int32_t *grown = nullptr;
+        CU(cudaMalloc((void **)&grown, (size_t)cap * sizeof(int32_t)));
+        if (c->eq_pending_n)
+            CU(cudaMemcpyAsync(grown, c->eq_pending, (size_t)c->eq_pending_n * sizeof(int32_t),
+                               cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->eq_pending) cudaFree(c->eq_pending);
+        c->eq_pending = grown;
+        c->eq_pending_cap = cap;
+    }
+    CU(cudaMemcpyAsync(c->eq_pending + c->eq_pending_n, c->list2, (size_t)n * sizeof(int32_t),
+                       cudaMemcpyDeviceToDevice, c->stream));
+    c->eq_pending_n += n;
+    return 0;
+}
+
 static int ensure_rho(bdr_ctx *c, int which) {
     if (c->rho[which]) return 0;
     CU(cudaMalloc((void **)&c->rho[which], (size_t)c->N * sizeof(double)));
@@ -447,10 +479,24 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
         } else {
             // label equality bits -> candidate bits (edge.cuh); voxels next to vacuum
             // are classified exactly from a list (checked for overflow below)
+            if (c->halo == 0 && c->eq_valid && c->eq_which == which && !getenv("BDR_EQ_RECOMPUTE")) {
+                // the equality bits of these labels exist; patch in what was relabelled since
+                // (the vacuum-seen flag of the pass that made them stays: a superset is fine)
+                TRY(zero_counter(c, CNT_DEFER));
+                if (c->eq_pending_n > 0)
+                    LAUNCH(c, BDR_K_EDGE_FLAG, k_eq_update, blocks_for(c->eq_pending_n, 128), 128, 0,
+                           c->labels[which], c->g, c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->eq_pending,
+                           c->eq_pending_n);
+                c->eq_pending_n = 0;
+            } else {
             CU(cudaMemsetAsync(c->d_cnt + CNT_DEFER, 0, 2 * sizeof(unsigned long long), c->stream));
             const dim3 ga((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
             LAUNCH(c, BDR_K_EDGE_FLAG, (k_label_eq_bits<4, EDGE_CX>), ga, 256, 0, c->labels[which], c->g,
                    c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->d_cnt + CNT_VACSEEN);
+            c->eq_valid = c->halo == 0;
+            c->eq_which = which;
+            c->eq_pending_n = 0;
+            }
             const dim3 gb((c->g.ny * c->nzw + 255) / 256, (c->g.nx + 15) / 16);
             LAUNCH(c, BDR_K_EDGE_FLAG, (k_edge_from_eq<16>), gb, 256, 0, c->eqz, c->eqy, c->eqx, c->vbits, c->g,
                    c->nzw, c->ebits, c->d_cnt + CNT_VACSEEN, c->d_cnt + CNT_DEFER, c->defer,
@@ -737,6 +783,7 @@ static int trace_dev(bdr_ctx *c, int which, const Weights &W, const TGrad &T, in
         }
     }
     *changed = (int64_t)c->h_cnt[CNT_CHANGED];
+    TRY(eq_note_changed(c, which, *changed, want_changed_list));
     c->escaped = (int64_t)c->h_cnt[CNT_ESCAPED];
     if (c->escaped && c->halo == 0) return fail_msg("trace: internal error (escape on a periodic grid)");
     c->trace_steps += (int64_t)c->h_cnt[CNT_STEPS];
@@ -1620,7 +1667,7 @@ int bdr_destroy(bdr_ctx *c) {
                     (void *)c->roots, (void *)c->minidx, (void *)c->rank, (void *)c->d_cnt,
                     (void *)c->d_sums, c->stage, (void *)c->ebits, (void *)c->term,
                     (void *)c->tile_keys, (void *)c->tile_order, (void *)c->tile_hist,
-                    (void *)c->d_seedw, (void *)c->defer, (void *)c->list4})
+                    (void *)c->d_seedw, (void *)c->defer, (void *)c->list4, (void *)c->eq_pending})
         if (p) cudaFree(p);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -1708,6 +1755,7 @@ int bdr_clear_labels(bdr_ctx *c, int which) {
     TRY(check(c));
     if (which < 0 || which > 1) return fail_msg("bdr_clear_labels: bad argument");
     c->maxima_fresh[which] = false;
+    eq_invalidate(c, which);
     TRY(ensure_labels(c, which));
     CU(cudaMemsetAsync(c->labels[which], 0, (size_t)c->N * sizeof(int32_t), c->stream));
     if (which == BDR_LABELS_BADER) c->vac_mode = VAC_NONE;
@@ -1718,6 +1766,7 @@ int bdr_upload_labels(bdr_ctx *c, int which, const void *host, int elem_size) {
     TRY(check(c));
     if (which < 0 || which > 1 || !host) return fail_msg("bdr_upload_labels: bad argument");
     c->maxima_fresh[which] = false;
+    eq_invalidate(c, which);
     TRY(ensure_labels(c, which));
     if (which == BDR_LABELS_BADER) c->vac_mode = VAC_LABELS;
     switch (elem_size) {
@@ -1765,6 +1814,7 @@ int bdr_vacuum_assign(bdr_ctx *c, double vac_tol, double voxel_volume, int which
     const double *dens = rho_ptr(c, which_density);
     if (!ref || !dens) return fail_msg("bdr_vacuum_assign: density not uploaded");
     c->maxima_fresh[0] = c->maxima_fresh[1] = false;
+    eq_invalidate(c, BDR_LABELS_BADER);
     TRY(ensure_labels(c, BDR_LABELS_BADER));
     TRY(ensure_sums(c, 2));
     CU(cudaMemsetAsync(c->d_sums, 0, sizeof(double), c->stream));
@@ -1801,6 +1851,7 @@ static int bader_calc_dev(bdr_ctx *c, int method, const double *dist_mat, const 
     const Weights W = make_weights(dist_mat);
     const int vac_mode_at_entry = c->vac_mode;
     c->maxima_fresh[0] = c->maxima_fresh[1] = false;
+    eq_invalidate(c, BDR_LABELS_BADER);
     TRY(choose_seed(c, method, W));
     int64_t seeded = -1;
     if (host_density) TRY(upload_and_stencil_dev(c, host_density, W, &seeded));
@@ -1907,6 +1958,7 @@ int bdr_assign_atoms(bdr_ctx *c, const double *maxima_cart, int64_t n_max, const
            c->labels[BDR_LABELS_ATOMS], c->N, c->rank);
     // the atom labels are the LUT image of the Bader labels: same vacuum voxels, same maxima
     c->maxima_fresh[BDR_LABELS_ATOMS] = c->maxima_fresh[BDR_LABELS_BADER];
+    eq_invalidate(c, BDR_LABELS_ATOMS);
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }

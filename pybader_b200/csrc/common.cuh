@@ -128,6 +128,12 @@ struct bdr_ctx {
     uint32_t *cbits = nullptr;  // scratch bit volume (voxels relabelled by the last trace)
     uint32_t *sbits = nullptr;  // sticky "was ever an edge or next to one" bits (conservative passes)
     uint32_t *eqz = nullptr, *eqy = nullptr, *eqx = nullptr;  // label equality bits (edge.cuh)
+    // the equality bits describe label set eq_which as of the last k_label_eq_bits pass; voxels
+    // relabelled since then wait in eq_pending and are patched in by k_eq_update (edge.cuh)
+    bool eq_valid = false;
+    int eq_which = -1;
+    int32_t *eq_pending = nullptr;
+    int64_t eq_pending_n = 0, eq_pending_cap = 0;
     int32_t *defer = nullptr;   // edge pass: voxels next to vacuum
     int64_t defer_cap = 0;
     int32_t *term = nullptr;    // where each traced voxel's trajectory ended (bader_calc('neargrid') only)

@@ -143,6 +143,39 @@ k_label_eq_bits(const int32_t *__restrict__ lab, Grid g, int nzw, uint32_t *__re
         label_eq_bits_body<WPT, CX, false>(lab, g, nzw, eqz, eqy, eqx, vbits, vac_seen, lane, j0, y, x0);
 }
 
+// Incremental maintenance of the four bit volumes: after a trace relabelled a few voxels, only
+// the bits that compare one of them with a neighbour can have changed -- eqz at z-1 and z, eqy
+// at y-1 and y, eqx at x-1 and x, and the voxel's own vacuum bit.  One thread per relabelled
+// voxel recomputes those seven bits from the current labels (two voxels that are neighbours
+// both write the shared bit, with the same value).  Replaces a full R 4 B/voxel pass when the
+// labels have not changed otherwise since the bits were made (renumbering keeps equalities).
+__device__ __forceinline__ void put_bit(uint32_t *vol, const Grid &g, int nzw, int x, int y, int z, bool on) {
+    uint32_t *w = vol + ((int64_t)x * g.ny + y) * nzw + (z >> 5);
+    const uint32_t m = 1u << (z & 31);
+    if (on) atomicOr(w, m);
+    else atomicAnd(w, ~m);
+}
+__global__ void __launch_bounds__(128)
+k_eq_update(const int32_t *__restrict__ lab, Grid g, int nzw, uint32_t *eqz, uint32_t *eqy, uint32_t *eqx,
+            uint32_t *vbits, const int32_t *__restrict__ list, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int v = list[t];
+    int x, y, z;
+    unlin3(g, v, x, y, z);
+    const int xm = x == 0 ? g.nx - 1 : x - 1, xp = x + 1 == g.nx ? 0 : x + 1;
+    const int ym = y == 0 ? g.ny - 1 : y - 1, yp = y + 1 == g.ny ? 0 : y + 1;
+    const int zm = z == 0 ? g.nz - 1 : z - 1, zp = z + 1 == g.nz ? 0 : z + 1;
+    const int32_t l = lab[v];
+    put_bit(eqz, g, nzw, x, y, z, l == lab[lin3(g, x, y, zp)]);
+    put_bit(eqz, g, nzw, x, y, zm, l == lab[lin3(g, x, y, zm)]);
+    put_bit(eqy, g, nzw, x, y, z, l == lab[lin3(g, x, yp, z)]);
+    put_bit(eqy, g, nzw, x, ym, z, l == lab[lin3(g, x, ym, z)]);
+    put_bit(eqx, g, nzw, x, y, z, l == lab[lin3(g, xp, y, z)]);
+    put_bit(eqx, g, nzw, xm, y, z, l == lab[lin3(g, xm, y, z)]);
+    put_bit(vbits, g, nzw, x, y, z, l == -1);
+}
+
 // Edge-candidate bits from the equality bits.  A thread owns one word position
 // (y, j) and marches along x: per plane it folds the 3 x 3 (y,z) patch into one
 // word P(x) (9 loads), and the candidate word of plane x is
