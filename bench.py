@@ -42,8 +42,9 @@ SHAPES = {1: (1024, 1024, 1024), 2: (2048, 1024, 1024), 4: (2048, 2048, 1024),
           8: (2048, 2048, 2048)}
 
 # algorithmic bytes per voxel of each streaming kernel family
-ALG_BYTES = {'stencil': 12, 'resolve': 8, 'relabel': 8, 'edge_flag': 5.125, 'edge_dilate': 1.25,
-             'first': 4, 'charge_sum': 12, 'vacuum': 12, 'narrow': 5}
+# edge_eq: labels R 4 + four bit volumes W 4/8; edge_flag (bits -> candidate bits): R 4/8 + W 1/8
+ALG_BYTES = {'stencil': 12, 'resolve': 8, 'relabel': 8, 'edge_eq': 4.5, 'edge_flag': 0.625,
+             'edge_dilate': 1.25, 'first': 4, 'charge_sum': 12, 'vacuum': 12, 'narrow': 5}
 
 
 def workload_case(shape):
@@ -301,13 +302,13 @@ def workload_name(shape, mode="('changed',2)"):
 # kernel names behind each family (for the DRAM traffic measured by ncu, profiles/*_traffic.json)
 FAMILY_KERNELS = {'trace': ['k_trace'], 'stencil': ['k_seed_pointers', 'k_ongrid_pointers'],
                   'resolve': ['k_resolve_tiles', 'k_tile_hist', 'k_tile_scan', 'k_tile_scatter'],
-                  'edge_flag': ['k_label_eq_bits', 'k_edge_from_eq', 'k_edge_deferred'],
+                  'edge_eq': ['k_label_eq_bits'], 'edge_flag': ['k_edge_from_eq', 'k_edge_deferred', 'k_eq_update'],
                   'edge_dilate': ['k_edge_known'], 'relabel': ['k_relabel_slots'],
                   'first': ['k_first_voxel_slots'], 'edge_confirm': ['k_edge_confirm']}
 
 
 # kernels launched per pass over the grid in the families that chain several kernels
-LAUNCHES_PER_PASS = {'resolve': 4, 'edge_flag': 3}
+LAUNCHES_PER_PASS = {'resolve': 4}
 
 
 def measured_traffic(family, n_voxels):
@@ -346,6 +347,8 @@ def kernel_accounting(prof, n_voxels, steps, tsteps, tvox, ms_per_step):
         if name in ALG_BYTES:
             gb = ALG_BYTES[name] * n_voxels * 1e-9
             passes = n / LAUNCHES_PER_PASS.get(name, 1)   # full passes over the grid
+            if name == 'edge_flag' and 'edge_dilate' in prof:
+                passes = prof['edge_dilate'][1]           # 2-3 small launches per pass; k_edge_known runs once
             k["alg_bytes_per_voxel"] = ALG_BYTES[name]
             k["passes_per_step"] = passes / steps
             k["achieved_gbs"] = gb / (ms / passes * 1e-3)

@@ -44,7 +44,7 @@ enum {
     BDR_K_STENCIL = 1,     /* 27-point stencil -> ascent pointers     */
     BDR_K_RESOLVE = 2,     /* pointer jumping to root codes           */
     BDR_K_RELABEL = 3,     /* slot -> volume-number LUT pass          */
-    BDR_K_EDGE_FLAG = 4,   /* edge classification stencil             */
+    BDR_K_EDGE_FLAG = 4,   /* edge candidates from the equality bits  */
     BDR_K_EDGE_DILATE = 5, /* near-edge dilation + compaction         */
     BDR_K_TRACE = 6,       /* neargrid trajectory re-trace of edges   */
     BDR_K_EDGE_CHECK = 7,  /* 'changed'-mode incremental reclassify   */
@@ -56,7 +56,8 @@ enum {
     BDR_K_FIRST = 13,      /* first-voxel (numbering) pass            */
     BDR_K_EDGE_CONFIRM = 14, /* edge candidates -> edges (density test) */
     BDR_K_TRACE_PEER = 15, /* sharded runs: walks continued on other ranks' memory */
-    BDR_K_COUNT = 16
+    BDR_K_EDGE_EQ = 16,    /* label equality bits: the streaming R 4 B/voxel half of the edge pass */
+    BDR_K_COUNT = 17
 };
 
 const char *bdr_last_error(void);

@@ -491,7 +491,7 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
             } else {
             CU(cudaMemsetAsync(c->d_cnt + CNT_DEFER, 0, 2 * sizeof(unsigned long long), c->stream));
             const dim3 ga((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
-            LAUNCH(c, BDR_K_EDGE_FLAG, (k_label_eq_bits<4, EDGE_CX>), ga, 256, 0, c->labels[which], c->g,
+            LAUNCH(c, BDR_K_EDGE_EQ, (k_label_eq_bits<4, EDGE_CX>), ga, 256, 0, c->labels[which], c->g,
                    c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->d_cnt + CNT_VACSEEN);
             c->eq_valid = c->halo == 0;
             c->eq_which = which;

@@ -18,7 +18,7 @@ MODES = {'all': 0, 'changed': 1}
 
 FAMILIES = ['vacuum', 'stencil', 'resolve', 'relabel', 'edge_flag', 'edge_dilate', 'trace',
             'edge_check', 'charge_sum', 'assign', 'surface', 'narrow', 'synth', 'first',
-            'edge_confirm', 'trace_peer']
+            'edge_confirm', 'trace_peer', 'edge_eq']
 
 
 def _f64(a):

@@ -58,11 +58,13 @@ def test_kernel_accounting_per_pass():
     sys.path.insert(0, ROOT)
     import bench as B
     N = 1024 ** 3
-    prof = {'stencil': (15.4, 2), 'edge_flag': (9.2, 18), 'resolve': (4.0, 8), 'trace': (35.0, 26)}
+    prof = {'stencil': (15.4, 2), 'edge_eq': (2.8, 2), 'edge_flag': (1.2, 14), 'edge_dilate': (4.6, 6),
+            'resolve': (4.0, 8), 'trace': (35.0, 26)}
     kernels, roof = B.kernel_accounting(prof, N, 2, 2 * 239_000_000, 2 * 79_000_000, 42.0)
     assert abs(kernels['stencil']['ms_per_step'] - 7.7) < 1e-9
     assert kernels['edge_flag']['passes_per_step'] == 3 and kernels['resolve']['passes_per_step'] == 1
-    gbs = 5.125 * N * 1e-9 / (9.2 / 6 * 1e-3)
-    assert abs(kernels['edge_flag']['achieved_gbs'] - gbs) < 1e-6 * gbs
+    assert kernels['edge_eq']['passes_per_step'] == 1
+    gbs = 4.5 * N * 1e-9 / (2.8 / 2 * 1e-3)
+    assert abs(kernels['edge_eq']['achieved_gbs'] - gbs) < 1e-6 * gbs
     assert roof['kernel'] == 'trace' and 0 < roof['frac'] < 1 and roof['bound'] == 'hbm'
     assert abs(roof['share_of_step'] - 17.5 / 42.0) < 1e-9
