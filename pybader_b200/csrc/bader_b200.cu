@@ -479,7 +479,7 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
         } else {
             // label equality bits -> candidate bits (edge.cuh); voxels next to vacuum
             // are classified exactly from a list (checked for overflow below)
-            if (c->halo == 0 && c->eq_valid && c->eq_which == which && !getenv("BDR_EQ_RECOMPUTE")) {
+            if (c->eq_valid && c->eq_which == which && !getenv("BDR_EQ_RECOMPUTE")) {
                 // the equality bits of these labels exist; patch in what was relabelled since
                 // (the vacuum-seen flag of the pass that made them stays: a superset is fine)
                 TRY(zero_counter(c, CNT_DEFER));
@@ -488,12 +488,28 @@ static int edge_find_dev(bdr_ctx *c, int which, int64_t *edges, int64_t n_change
                            c->labels[which], c->g, c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->eq_pending,
                            c->eq_pending_n);
                 c->eq_pending_n = 0;
+                if (c->halo > 0) {
+                    // a slab's halo labels come from its neighbours (halo exchanges): the bit planes
+                    // that compare with them -- the halos and the owned plane next to each -- are
+                    // recomputed, 2 * (halo + 1) planes instead of the whole window
+                    const int H = c->halo, Wp = c->g.nx;
+                    const int lo_end = std::min(H + 1, Wp), hi_begin = std::max(Wp - H - 1, lo_end);
+                    const dim3 gl((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (lo_end + EDGE_CX - 1) / EDGE_CX);
+                    LAUNCH(c, BDR_K_EDGE_EQ, (k_label_eq_bits<4, EDGE_CX>), gl, 256, 0, c->labels[which], c->g,
+                           c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->d_cnt + CNT_VACSEEN, 0, lo_end);
+                    if (hi_begin < Wp) {
+                        const dim3 gh((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (Wp - hi_begin + EDGE_CX - 1) / EDGE_CX);
+                        LAUNCH(c, BDR_K_EDGE_EQ, (k_label_eq_bits<4, EDGE_CX>), gh, 256, 0, c->labels[which],
+                               c->g, c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->d_cnt + CNT_VACSEEN,
+                               hi_begin, Wp);
+                    }
+                }
             } else {
             CU(cudaMemsetAsync(c->d_cnt + CNT_DEFER, 0, 2 * sizeof(unsigned long long), c->stream));
             const dim3 ga((c->nzw + 3) / 4, (c->g.ny + 7) / 8, (c->g.nx + EDGE_CX - 1) / EDGE_CX);
             LAUNCH(c, BDR_K_EDGE_EQ, (k_label_eq_bits<4, EDGE_CX>), ga, 256, 0, c->labels[which], c->g,
-                   c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->d_cnt + CNT_VACSEEN);
-            c->eq_valid = c->halo == 0;
+                   c->nzw, c->eqz, c->eqy, c->eqx, c->vbits, c->d_cnt + CNT_VACSEEN, 0, c->g.nx);
+            c->eq_valid = true;
             c->eq_which = which;
             c->eq_pending_n = 0;
             }
@@ -1185,6 +1201,7 @@ int bdr_slab_seed(bdr_ctx *c, const double *dist_mat, int64_t *n_real, int64_t *
     int64_t n = 0;
     const int vac_mode_at_entry = c->vac_mode;
     c->maxima_fresh[0] = c->maxima_fresh[1] = false;
+    eq_invalidate(c, BDR_LABELS_BADER);
     TRY(choose_seed(c, c->slab_seed_method, W));
     TRY(stencil_dev(c, W, &n));
     TRY(resolve_dev(c, nullptr));
@@ -1209,6 +1226,7 @@ int bdr_slab_first_voxel(bdr_ctx *c, int64_t n_slots, int32_t *dev_out) {
 
 int bdr_slab_apply_rank(bdr_ctx *c, const int32_t *dev_rank) {
     TRY(check(c));
+    eq_invalidate(c, BDR_LABELS_BADER);   // exit slots and maxima slots may share a volume number
     LAUNCH(c, BDR_K_RELABEL, k_relabel_slots, blocks_for(c->N, 1024), 256, 0,
            c->labels[BDR_LABELS_BADER], c->N, dev_rank);
     c->vac_mode = VAC_LABELS;

@@ -32,9 +32,9 @@ __device__ __forceinline__ void label_eq_bits_body(const int32_t *__restrict__ l
                                                    uint32_t *__restrict__ eqz, uint32_t *__restrict__ eqy,
                                                    uint32_t *__restrict__ eqx, uint32_t *__restrict__ vbits,
                                                    unsigned long long *vac_seen, int lane, int j0, int y,
-                                                   int x0) {
+                                                   int x0, int x_end) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int nplanes = min(CX, g.nx - x0);
+    const int nplanes = min(CX, x_end - x0);
     const int plane = g.ny * g.nz;
     const int z0 = 32 * j0 + lane;  // word i of the segment holds voxel z0 + 32 i of this lane
     bool ok[WPT];
@@ -133,14 +133,16 @@ template <int WPT, int CX>
 __global__ void __launch_bounds__(256)
 k_label_eq_bits(const int32_t *__restrict__ lab, Grid g, int nzw, uint32_t *__restrict__ eqz,
                 uint32_t *__restrict__ eqy, uint32_t *__restrict__ eqx,
-                uint32_t *__restrict__ vbits, unsigned long long *vac_seen) {
+                uint32_t *__restrict__ vbits, unsigned long long *vac_seen, int x_begin, int x_end) {
+    // planes [x_begin, x_end): the whole grid, or the few planes next to a slab's halos whose
+    // labels an exchange has just replaced
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int j0 = blockIdx.x * WPT, y = blockIdx.y * 8 + w, x0 = blockIdx.z * CX;
-    if (y >= g.ny) return;  // the whole warp; the kernel has no barriers
+    const int j0 = blockIdx.x * WPT, y = blockIdx.y * 8 + w, x0 = x_begin + blockIdx.z * CX;
+    if (y >= g.ny || x0 >= x_end) return;  // the whole warp; the kernel has no barriers
     if (32 * (j0 + WPT) <= g.nz)
-        label_eq_bits_body<WPT, CX, true>(lab, g, nzw, eqz, eqy, eqx, vbits, vac_seen, lane, j0, y, x0);
+        label_eq_bits_body<WPT, CX, true>(lab, g, nzw, eqz, eqy, eqx, vbits, vac_seen, lane, j0, y, x0, x_end);
     else
-        label_eq_bits_body<WPT, CX, false>(lab, g, nzw, eqz, eqy, eqx, vbits, vac_seen, lane, j0, y, x0);
+        label_eq_bits_body<WPT, CX, false>(lab, g, nzw, eqz, eqy, eqx, vbits, vac_seen, lane, j0, y, x0, x_end);
 }
 
 // Incremental maintenance of the four bit volumes: after a trace relabelled a few voxels, only
