@@ -23,9 +23,11 @@ with open(os.path.join(P, f'{tag}_traffic.json')) as f:
     tr = json.load(f)
 N = 1024 ** 3
 fam_k = {'stencil': ['k_seed_pointers'], 'resolve': ['k_tile_hist', 'k_tile_scan', 'k_tile_scatter', 'k_resolve_tiles'],
-         'relabel': ['k_relabel_slots'], 'edge_flag': ['k_label_eq_bits', 'k_edge_from_eq', 'k_edge_deferred'],
+         'relabel': ['k_relabel_slots'], 'edge_eq': ['k_label_eq_bits'],
+         'edge_flag': ['k_edge_from_eq', 'k_edge_deferred', 'k_eq_update'],
          'edge_dilate': ['k_edge_known'], 'trace': ['k_trace'], 'first': ['k_first_voxel_slots'],
-         'edge_confirm': ['k_edge_confirm', 'k_edge_fix_clear', 'k_edge_fix_known', 'k_edge_fix_tomb'],
+         'edge_confirm': ['k_edge_confirm', 'k_edge_confirm_roots', 'k_edge_fix_clear', 'k_edge_fix_known',
+                          'k_edge_fix_tomb', 'k_mark_interior'],
          'edge_check': ['k_filter_cached', 'k_inc_collect', 'k_inc_classify', 'k_inc_dilate', 'k_inc_mark',
                         'k_compact_known', 'k_bits_from_list', 'k_ec_init', 'k_ec_round', 'k_ec_collect_centres',
                         'k_ec_classify', 'k_ec_dilate', 'k_ec_finish']}
@@ -42,10 +44,22 @@ w(f"| step, density resident (`value`) | {b['ms_per_step']:.2f} ms → {b['value
 e = b['e2e']
 w(f"| end to end through `bdr_run`, host buffers (`e2e`) | {e['ms_per_step']:.1f} ms → {e['value'] / 1e9:.2f} Gvoxel/s "
   f"({e['h2d_bytes_per_step'] / 1e9:.2f} GB H2D + {e['d2h_bytes_per_step'] / 1e9:.2f} GB D2H per step; PCIe-bound) |")
+h = e.get('handlers')
+if h:
+    w(f"| end to end through `thread_handlers.bader_calc` + `refine` (what the unmodified `Bader` drives; pageable numpy, "
+      f"fresh session per step) | {h['ms_per_step']:.0f} ms → {h['value'] / 1e9:.2f} Gvoxel/s |")
 c = b['cpu_baseline']
 if c:
-    w(f"| CPU oracle port, 1 core (`cpu_baseline`) | {c['value'] / 1e6:.2f} Mvoxel/s ({c['sample'].split(',')[0]}) |")
-w(f"| reference arm (`--impl reference`, {ref['cpu_baseline']['cores']} host threads) | {ref['value'] / 1e6:.1f} Mvoxel/s |")
+    w(f"| `cpu_baseline` (kind `{c['kind']}`, {c['cores']} host threads) | {c['value'] / 1e6:.2f} Mvoxel/s — {c['sample']} |")
+rc = ref['cpu_baseline']
+w(f"| reference arm (`--impl reference`, kind `{rc['kind']}`, {rc['cores']} host threads) | {ref['value'] / 1e6:.2f} Mvoxel/s — "
+  f"{rc['sample']} |")
+for tagw, label in (('c3', 'BASELINE config 3'), ('c4', 'BASELINE config 4')):
+    fw = os.path.join(P, f'{tag}_bench_{tagw}.json')
+    if os.path.exists(fw):
+        dw = load(f'{tag}_bench_{tagw}.json')
+        w(f"| {label} (`bench.py --workload {tagw}`) | {dw['ms_per_step']:.2f} ms → {dw['value'] / 1e9:.2f} Gvoxel/s; e2e "
+          f"{dw['e2e']['ms_per_step']:.1f} ms; {dw['config']['maxima']} maxima, refine history {dw['refine_history_last_step']} |")
 w(f"| kernels launched per step (`gpu_launches` / steps) | {b['gpu_launches'] / b['steps']:.0f} |")
 w(f"| SM clock during the timed region | {b['clocks']['sm_mhz']} MHz of {b['clocks']['sm_max_mhz']} (reasons: {b['clocks']['reasons'] or 'none'}) |")
 r = b['roofline']
@@ -102,12 +116,16 @@ for n in (2, 4, 8):
     if not os.path.exists(f):
         continue
     d = load(f'{tag}_bench_n{n}.json')
+    km = d.get('kernel_ms_per_step', {})
     w(f"| {n} | {d['config']['workload'].split(' ')[0]} | {d['ms_per_step']:.2f} | {d['value'] / 1e9:.1f} | "
-      f"{d['e2e']['value'] / 1e9:.2f} | {sum(k['ms_per_step'] for k in d['kernels'].values()):.1f} | "
-      f"refine ('all', 2): one more full edge pass + trace than N = 1; {d.get('neargrid_passes')} rounds, "
-      f"{d.get('exit_rounds')} exit rounds |")
-w("\nThe N > 1 step is a heavier algorithm than the N = 1 step (DESIGN.md section 7) and is driven from Python "
-  "with an all-reduce per round; the gap between the kernel sum and the step is that protocol.\n")
+      f"{d['e2e']['value'] / 1e9:.2f} | {sum(k['ms_per_step'] for k in d['kernels'].values()):.1f} "
+      f"(slowest rank {km.get('max_over_ranks', 0):.1f}) | "
+      f"refine {tuple(d['config']['refine_mode'])}, history {d['refine_history_last_step']}; {d.get('neargrid_passes')} rounds, "
+      f"{d.get('exit_rounds')} exit rounds; efficiency vs N=1 {b['ms_per_step'] / d['ms_per_step']:.2f} |")
+w("\nEvery N runs the same algorithm (`refine(('changed', 2))`); the round loops run inside the library over its own NCCL "
+  "communicator (DESIGN.md section 7).  The gap between the kernel sum and the step is exit resolution / numbering in "
+  "torch, the wait for the slowest rank of every round and the host decisions per round.  Parity of the sharded runs: "
+  "`*_sharded_w{2,4,8}_pytest.log`, `*_sharded_handlers_w2_pytest.log`.\n")
 w("## Files\n")
 for f in sorted(os.listdir(P)):
     if f == 'README.md':
@@ -116,7 +134,15 @@ for f in sorted(os.listdir(P)):
             'launches_1024.csv': "ncu launch list (gpu__time_duration.sum) of `bench.py --steps 1 --warmup 3`",
             'traffic.json': "DRAM bytes and duration of every launch of one step (tools/ncu_traffic.py)",
             'ncu_set_full_1024.txt': "key metrics of the `--set full` captures of the top kernels (tools/ncu_summary.py)",
-            'pytest_gpu.log': "`pytest -m gpu` on the box", 'smoke.log': "`__graft_entry__.smoke()`",
+            'pytest_gpu.log': "`pytest -m gpu -s -rs` on a one-GPU box (the multi-GPU cases skip there)",
+            'smoke.log': "`__graft_entry__.smoke()`",
+            'bench_c3.json': "bench.py --workload c3 (BASELINE config 3 shape)",
+            'bench_c4.json': "bench.py --workload c4 (BASELINE config 4 shape)",
+            'sharded_w2_pytest.log': "`pytest tests/test_gpu_sharded.py` under `gpurun --gpus 2`: 2 ranks vs 1 GPU, library and Python loops, unmodified Bader over 2 ranks",
+            'sharded_w4_pytest.log': "the same under `gpurun --gpus 4` (2- and 4-rank cases)",
+            'sharded_w8_pytest.log': "the 8-rank case under `gpurun --gpus 8`",
+            'sharded_handlers_w2_pytest.log': "first run of the unmodified `Bader.__call__` over 2 ranks",
+            'trace_occupancy.txt': "A/B of k_trace launch bounds and refill chunk",
             'sanitizer_memcheck.log': "compute-sanitizer memcheck over smoke(): 0 errors",
             'sanitizer_racecheck.log': "compute-sanitizer racecheck over smoke(): the intended in-tile chase race only (DESIGN.md section 8)",
             'io_bench_256.json': "tools/io_bench.py: CHGCAR reader (GPU text -> grid) next to the reference's conversion"}
