@@ -43,7 +43,14 @@ class ModelBackend:
             self.lab[self.rho <= vac_tol] = -1
         self._labels_t = torch.from_numpy(self.lab)
         self.own_lo, self.own_hi = halo * self.plane, (self.shape[0] - halo) * self.plane
-        self.known = None
+        self._known = np.zeros(self.shape, dtype=np.int8)
+        self._known_t = torch.from_numpy(self._known)
+        self.changed = np.zeros(0, dtype=np.int64)
+        # global scan order of edge_check's centre selection: set by the test (ShardedBader knows it)
+        self.x0w, self.NX = 0, self.shape[0]
+
+    def known(self):
+        return self._known_t
 
     def labels(self):
         return self._labels_t
@@ -95,15 +102,104 @@ class ModelBackend:
         flat[sel] = lut[-2 - flat[sel].astype(np.int64)]
 
     def edge_pass(self):
-        self.known = np.zeros(self.shape, dtype=np.int8)
-        orc.edge_find(self.known, self.rho, self.lab)
-        return int((self.known.reshape(-1)[self.own_lo:self.own_hi] == -2).sum())
+        self._known[...] = 0
+        orc.edge_find(self._known, self.rho, self.lab)
+        return int((self._known.reshape(-1)[self.own_lo:self.own_hi] == -2).sum())
 
     def trace_pass(self, dist_mat, T_grad, want_list=False):
         before = self.lab.reshape(-1)[self.own_lo:self.own_hi].copy()
-        orc.refine_neargrid(self.known, self.known.copy(), self.rho, self.lab, dist_mat, T_grad)
+        orc.refine_neargrid(self._known, self._known.copy(), self.rho, self.lab, dist_mat, T_grad)
         after = self.lab.reshape(-1)[self.own_lo:self.own_hi]
+        self.changed = np.flatnonzero(before != after) + self.own_lo if want_list else np.zeros(0, np.int64)
         return int((before != after).sum()), 0
+
+    # ---- refinement.edge_check (refinement.py:409-508) in the phases the ranks exchange between;
+    # a direct numpy restatement of the kernels k_ec_* (loops over the short changed list)
+    def _unlin(self, v):
+        nx, ny, nz = self.shape
+        return v // (ny * nz), (v // nz) % ny, v % nz
+
+    def _nbrs(self, v):
+        nx, ny, nz = self.shape
+        x, y, z = self._unlin(v)
+        for ix, iy, iz in itertools.product((-1, 0, 1), repeat=3):
+            yield ((x + ix) % nx, (y + iy) % ny, (z + iz) % nz)
+
+    def _gidx(self, p):
+        gx = (p[0] + self.x0w) % self.NX
+        return (gx * self.shape[1] + p[1]) * self.shape[2] + p[2]
+
+    def _classify(self, p):
+        """0 not an edge, 1 edge and not a maximum, 2 edge and maximum (vacuum neighbours ignored)"""
+        mine, here = self.lab[p], self.rho[p]
+        e, m = False, True
+        for q in self._nbrs((p[0] * self.shape[1] + p[1]) * self.shape[2] + p[2]):
+            l = self.lab[q]
+            if l == -1:
+                continue
+            e |= l != mine
+            m &= not self.rho[q] > here
+        return (2 if m else 1) if e else 0
+
+    def ec_begin(self):
+        for v in self.changed:
+            p = self._unlin(int(v))
+            if self._classify(p) == 2:
+                self._known[p] = -4
+
+    def ec_round(self):
+        new, undecided = {}, 0
+        for v in self.changed:
+            p = self._unlin(int(v))
+            if self._known[p] != -2:
+                continue
+            gv = self._gidx(p)
+            out = blocked = False
+            for q in self._nbrs(int(v)):
+                if self._gidx(q) >= gv:
+                    continue
+                k = self._known[q]
+                out |= k == -4
+                blocked |= k == -2
+            if out:
+                new[p] = -5
+            elif not blocked:
+                new[p] = -4
+            else:
+                undecided += 1
+        for p, k in new.items():
+            self._known[p] = k
+        return undecided
+
+    def ec_finish(self):
+        W, H = self.shape[0], self.halo
+        centres = [self._unlin(int(v)) for v in self.changed if self._known[self._unlin(int(v))] == -4]
+        for xs in (range(1, H), range(W - H, W - 1)):
+            for x in xs:
+                for y, z in zip(*np.nonzero(self._known[x] == -4)):
+                    centres.append((x, int(y), int(z)))
+        new_edges = []
+        for c in centres:
+            for pe in self._nbrs((c[0] * self.shape[1] + c[1]) * self.shape[2] + c[2]):
+                cls = self._classify(pe)
+                if cls == 0:
+                    self._known[pe] = -1
+                elif cls == 1 and self._known[pe] != -3:
+                    self._known[pe] = -3
+                    new_edges.append(pe)
+        for e in new_edges:
+            for q in self._nbrs((e[0] * self.shape[1] + e[1]) * self.shape[2] + e[2]):
+                if self._known[q] >= 0:
+                    self._known[q] = -1
+        owned = 0
+        for e in new_edges:
+            self._known[e] = -2
+            lin = (e[0] * self.shape[1] + e[1]) * self.shape[2] + e[2]
+            owned += self.own_lo <= lin < self.own_hi
+        for c in centres:
+            if self._known[c] == -4:
+                self._known[c] = -2
+        return owned
 
     def charge_sum(self, n, dV, which_density=0):
         q, v = np.zeros(n), np.zeros(n)

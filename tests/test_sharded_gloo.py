@@ -57,14 +57,22 @@ def _worker(rank, world, port, vac, halo, out):
         sb = ShardedBader.__new__(ShardedBader)
         holder['sb'] = sb
         ShardedBader.__init__(sb, rho.shape, comm, factory, halo=halo)
+        sb.backend.x0w, sb.backend.NX = sb.x0 - halo, rho.shape[0]
         mx = sb.ongrid(dm)
         lab_on = sb.owned_labels().numpy().copy()
         hist = sb.refine(dm, T, -1)
         lab_ng = sb.owned_labels().numpy().copy()
         n = mx.shape[0]
         q, v = sb.charge_sum(n, dV)
+        # 'changed'-mode refinement across the slabs, from the same ongrid labels
+        sb.backend.lab[...] = 0
+        if tol is not None:
+            sb.backend.lab[sb.backend.rho <= tol] = -1
+        sb.ongrid(dm)
+        hist_c = sb.refine(dm, T, 3, mode='changed')
+        lab_c = sb.owned_labels().numpy().copy()
         np.savez(os.path.join(out, f'r{rank}.npz'), x0=sb.x0, x1=sb.x1, maxima=mx, lab_on=lab_on,
-                 lab_ng=lab_ng, hist=np.array(hist), q=q, v=v)
+                 lab_ng=lab_ng, hist=np.array(hist), q=q, v=v, lab_c=lab_c, hist_c=np.array(hist_c))
     finally:
         dist.destroy_process_group()
 
@@ -92,6 +100,13 @@ def test_sharded_matches_single(tmp_path, world, vac):
     np.testing.assert_array_equal(lab_on, ref_on)                # ongrid: bit-exact, same numbering
     np.testing.assert_array_equal(lab_ng, ref_ng)                # Jacobi passes: partition independent
     assert [tuple(h) for h in parts[0]['hist']][:len(log)] == log[:len(parts[0]['hist'])]
+    # 'changed' mode: edge_check's centre selection follows the global scan order
+    ref_c = ref_on.astype(np.int32)
+    log_c = []
+    orc.refine('neargrid', ('changed', 3), rho, ref_c, dm, T, log=log_c)
+    lab_c = np.concatenate([p['lab_c'] for p in parts], axis=0)
+    np.testing.assert_array_equal(lab_c, ref_c)
+    assert [tuple(h) for h in parts[0]['hist_c']] == log_c, (parts[0]['hist_c'], log_c)
     n = mx.shape[0]
     q, v = np.zeros(n), np.zeros(n)
     orc.charge_sum(q, v, dV, rho, ref_ng)
