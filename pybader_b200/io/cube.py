@@ -13,88 +13,84 @@ bohr_to_ang = 0.52917721067
 ang_to_bohr = 1 / bohr_to_ang
 
 
+class _Header:
+    """Everything a cube file says before its volumetric block (io/cube.py:45-98), pulled
+    from a token stream so that the layout of the header lines does not matter."""
+
+    def __init__(self, f):
+        f.readline(), f.readline()                      # two comment lines
+        first = f.readline().split()
+        self.atom_sum = int(first[0])                   # negative: a data-set id line follows the atoms
+        self.nval = int(first[5]) if len(first) > 4 else 1   # (the origin, first[1:4], is ignored by the reference)
+        n_atoms = abs(self.atom_sum)
+        axes = np.array([f.readline().split() for _ in range(3)], dtype=np.float64)
+        self.grid = axes[:, 0].astype(np.int64)
+        self.lattice = axes[:, 1:4] * axes[:, :1]       # voxel vectors times the voxel counts
+        rows = [f.readline().split() for _ in range(n_atoms)]
+        self.atom_types = np.array([r[0] for r in rows], dtype=np.int64).reshape(n_atoms)
+        pos = np.array([r[-3:] for r in rows], dtype=np.float64).reshape(n_atoms, 3)
+        frac = np.dot(pos, np.linalg.inv(self.lattice))
+        frac %= 1
+        self.atoms = np.dot(frac, self.lattice)         # wrapped into the cell, still in Bohr
+        self.dset_ids = None
+        if self.atom_sum < 0:
+            ids = f.readline().split()
+            self.nval = int(ids.pop(0))
+            while len(ids) < self.nval:                 # the id list may run over several lines
+                ids += f.readline().split()
+            self.dset_ids = [int(m) for m in ids[:self.nval]]
+
+
+def _select_orbitals(values, hdr, orbitals):
+    """what `orbitals` asks of a file with several values per voxel (io/cube.py:114-141);
+    values is [nval][nx][ny][nz]"""
+    if hasattr(orbitals, '__iter__'):
+        return np.sum([values[hdr.dset_ids.index(int(m))] for m in orbitals], axis=0)
+    if orbitals < 0:
+        return values
+    if orbitals > 0:
+        return values[hdr.dset_ids.index(int(orbitals))].copy()
+    if hdr.atom_sum > 0:
+        return values[0].copy()
+    return np.sum(values, axis=0)
+
+
 def read(fn, orbitals=0, device=0):
-    """Read the charge density from a cube file (io/cube.py:18-156)."""
+    """Read the charge density from a cube file (io/cube.py:18-156): same arguments, same
+    return tuple, same units (Bohr -> Angstrom, values * bohr^-3)."""
     t0 = time()
-    density = dict()
-    prefix, filename = os.path.split(fn)
-    prefix = os.path.join(prefix, '')
+    prefix = os.path.join(os.path.split(fn)[0], '')
     with open(fn, 'rb') as f:
         print(f"  Reading {fn} as cube format.")
-        _ = f.readline()
-        _ = f.readline()
-        line = f.readline().split()
-        atom_sum = int(line[0])
-        origin = np.array(line[1:4], dtype=np.float64)  # noqa: F841 (ignored by the reference too)
-        nval = int(line[5]) if len(line) > 4 else 1
-        grid = np.zeros(3, dtype=np.int64)
-        lattice = np.zeros((3, 3), dtype=np.float64)
-        for i in range(3):
-            line = f.readline().split()
-            grid[i] = line[0]
-            lattice[i] = line[1:]
-            lattice[i] *= grid[i]
-        print(f"  {' x '.join(grid.astype(str))} grid size.")
-        atom_types = np.zeros(abs(atom_sum), dtype=np.int64)
-        atoms = np.zeros((abs(atom_sum), 3), dtype=np.float64)
-        for i in range(abs(atom_sum)):
-            line = f.readline().split()
-            atom_types[i] = line[0]
-            atoms[i] = line[-3:]
-        atoms = np.dot(atoms, np.linalg.inv(lattice))
-        atoms %= 1
-        atoms = np.dot(atoms, lattice)
-        dset_ids = None
-        if atom_sum < 0:
-            line = f.readline().split()
-            dset_ids = np.zeros(int(line.pop(0)), dtype=np.int64)
-            nval = dset_ids.shape[0]
-            count = 0
-            while count < nval:
-                for m in line:
-                    dset_ids[count] = m
-                    count += 1
-                line = f.readline().split() if count < nval else line
-        nx, ny, nz = (int(g) for g in grid)
-        buf = np.fromfile(f, dtype=np.uint8)
-    # the file runs z (and the nval values of a voxel) fastest: already C order
-    # (with one value per voxel the unit conversion, io/cube.py:143, rides along)
-    if nval == 1:
-        charge, _ = parse_block(buf, (nx, ny, nz), False, OP_MULTIPLY, ang_to_bohr**3, device)
+        hdr = _Header(f)
+        print(f"  {' x '.join(hdr.grid.astype(str))} grid size.")
+        block = np.fromfile(f, dtype=np.uint8)
+    nx, ny, nz = (int(g) for g in hdr.grid)
+    # the file runs z (and the nval values of a voxel) fastest: already C order; with one
+    # value per voxel the unit conversion (io/cube.py:143) rides along in the conversion
+    if hdr.nval == 1:
+        charge, _ = parse_block(block, (nx, ny, nz), False, OP_MULTIPLY, ang_to_bohr**3, device)
     else:
-        charge, _ = parse_block(buf, (nx, ny, nz * nval), False, OP_NONE, 1.0, device)
-    del buf
+        raw, _ = parse_block(block, (nx, ny, nz * hdr.nval), False, OP_NONE, 1.0, device)
+        charge = _select_orbitals(np.swapaxes(raw.reshape(nx, ny, nz, hdr.nval), 0, -1), hdr, orbitals)
+        charge *= ang_to_bohr**3
+    del block
     print(f"  File {fn} closed. ", end='')
-    if nval > 1:
-        ids = list(dset_ids) if dset_ids is not None else None
-        charge = np.swapaxes(charge.reshape(nx, ny, nz, nval), 0, -1)
-        if hasattr(orbitals, '__iter__'):
-            density['charge'] = np.sum([charge[ids.index(int(m))] for m in orbitals], axis=0)
-        elif orbitals < 0:
-            density['charge'] = charge
-        elif orbitals > 0:
-            density['charge'] = charge[ids.index(int(orbitals))].copy()
-        elif atom_sum > 0:
-            density['charge'] = charge[0].copy()
-        else:
-            density['charge'] = np.sum(charge, axis=0)
-        del charge
-    else:
-        density['charge'] = charge
     print(f"Time taken: {time() - t0:0.3f}s", end='\n\n')
-    lattice *= bohr_to_ang
-    atoms *= bohr_to_ang
-    if nval > 1:
-        density['charge'] *= ang_to_bohr**3
-    file_info = {
-        'filename': fn,
-        'prefix': prefix,
-        'file_type': 'cube',
-        'write_function': write,
-        'elements': atom_types,
-        'voxel_offset': np.array([.5, .5, .5])
-    }
-    return density, lattice, atoms, file_info
+    file_info = dict(filename=fn, prefix=prefix, file_type='cube', write_function=write,
+                     elements=hdr.atom_types, voxel_offset=np.array([.5, .5, .5]))
+    return {'charge': charge}, hdr.lattice * bohr_to_ang, hdr.atoms * bohr_to_ang, file_info
+
+
+def _fixed(lead, row, prec):
+    """one header line: `lead`, then three coordinates, each 10 wide with `prec` decimals
+    (as many as the widest entry of the table leaves room for, io/cube.py:190-195)"""
+    return lead + ''.join(f" {v:> 10.{prec}f}" for v in row) + '\n'
+
+
+def _precision(table):
+    width = max(int(np.max(np.log10(np.abs(table[table != 0]))) + 9), 9) + 1
+    return 17 - width
 
 
 def write(fn, atoms, lattice, density, file_info, prefix=None, suffix='.cube'):
@@ -102,43 +98,28 @@ def write(fn, atoms, lattice, density, file_info, prefix=None, suffix='.cube'):
     Like the reference, `atoms`, `lattice` and the charge array are converted to Bohr
     units IN PLACE (io/cube.py:183-187)."""
     from ._format import append_block, fortran_lines
-    if prefix is not None:
-        fn = prefix + fn
-    fn += suffix
+    path = (prefix or '') + fn + suffix
     fmt = file_info.get('fortran_format', 0)
     charge = density['charge']
     atoms *= ang_to_bohr
     charge *= bohr_to_ang**3
     lattice *= ang_to_bohr
     lattice /= charge.shape
-    lattice_width = np.max(np.log10(np.abs(lattice[lattice != 0]))) + 9
-    lattice_width = max([int(lattice_width), 9]) + 1
-    lattice_prec = 17 - lattice_width
-    atoms_width = np.max(np.log10(np.abs(atoms[atoms != 0]))) + 9
-    atoms_width = max([int(atoms_width), 9]) + 1
-    atoms_prec = 17 - atoms_width
-    with open(fn, 'w') as f:
-        f.write("Cube File writen in pybader\n")
-        f.write(file_info['comment'])
-        f.write(f"{atoms.shape[0]:>5}{'  0.0000000'*3}\n")
-        for i, lat in enumerate(lattice):
-            x, y, z = lat
-            f.write(f"{charge.shape[i]:>5}")
-            f.write(f" {x:> {10}.{lattice_prec}f} {y:> {10}.{lattice_prec}f} {z:> {10}.{lattice_prec}f}\n")
-        for i, atom in enumerate(atoms):
-            x, y, z = atom
-            f.write(f"{file_info['elements'][i]:>5}")
-            f.write('  0.0000000')
-            f.write(f" {x:> {10}.{atoms_prec}f} {y:> {10}.{atoms_prec}f} {z:> {10}.{atoms_prec}f}\n")
+    lat_prec, atom_prec = _precision(lattice), _precision(atoms)
+    head = ["Cube File writen in pybader\n", file_info['comment'],
+            f"{atoms.shape[0]:>5}{'  0.0000000' * 3}\n"]
+    head += [_fixed(f"{n:>5}", vec, lat_prec) for n, vec in zip(charge.shape, lattice)]
+    head += [_fixed(f"{el:>5}  0.0000000", xyz, atom_prec) for el, xyz in zip(file_info['elements'], atoms)]
+    with open(path, 'w') as f:
+        f.writelines(head)
         if fmt == 2:
+            # utils.fortran_format: six values per line, a shorter last line per z row
             nz = charge.shape[2]
             full = nz // 6 * 6
-            for i in range(charge.shape[0]):
-                for j in range(charge.shape[1]):
-                    row = charge[i, j]
-                    if full:
-                        f.write(fortran_lines(row[:full].reshape(-1, 6), 5))
-                    if full < nz:
-                        f.write(fortran_lines(row[full:].reshape(1, -1), 5))
+            for row in charge.reshape(-1, nz):
+                if full:
+                    f.write(fortran_lines(row[:full].reshape(-1, 6), 5))
+                if full < nz:
+                    f.write(fortran_lines(row[full:].reshape(1, -1), 5))
     if fmt != 2:
-        append_block(fn, charge, False, charge.shape[2], 6, 5, fmt == 1)
+        append_block(path, charge, False, charge.shape[2], 6, 5, fmt == 1)

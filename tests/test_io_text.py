@@ -172,3 +172,16 @@ def test_fallback_tokens_longer_than_64_bytes():
     junk = '1.' + '0' * 70 + 'x'
     with pytest.raises(ValueError):
         parse_block(f"1.5 {junk} -2.25 4.0\n".encode(), (1, 2, 2), False)
+
+
+@pytest.mark.parametrize('name', ['a.cube', 'b.cube'])
+def test_cube_header_matches_reference_reader(name, golden):
+    """the header half of cube.read needs no GPU: lattice, atoms and elements as the real
+    reference reader returned them (tests/golden_io/make_io_golden.py)"""
+    from pybader_b200.io import cube
+    with open(os.path.join(GOLDEN, name), 'rb') as f:
+        hdr = cube._Header(f)
+    np.testing.assert_array_equal(hdr.lattice * cube.bohr_to_ang, golden[f'{name}_lattice'])
+    np.testing.assert_array_equal(hdr.atoms * cube.bohr_to_ang, golden[f'{name}_atoms'])
+    np.testing.assert_array_equal(hdr.atom_types, golden[f'{name}_elements'])
+    assert tuple(hdr.grid) == golden[f'{name}_charge'].shape[-3:] or hdr.nval > 1
