@@ -160,3 +160,19 @@ def test_handlers_dispatch_to_the_sharded_engine_under_torchrun(monkeypatch):
                      'charge_sum', 'volume_mask']
     monkeypatch.setenv('BDR_FORCE_SINGLE', '1')
     assert not sh.active()
+
+
+def test_geometry_helper_is_bit_exact_against_the_reference_bader():
+    """pybader_b200/geometry.py (what tests and bench.py hand to the engine) reproduces
+    Bader.distance_matrix / T_grad / voxel_volume (interface.py:242-290) bit for bit: golden
+    values stored by tests/golden_call/make_call_golden.py from the real `Bader` object
+    (cubic, triclinic and orthorhombic cells)"""
+    from pybader_b200 import geometry as geo
+    gdir = os.path.join(ROOT, 'tests', 'golden_call')
+    shapes = {'c1_default': (96, 96, 96), 'ref_spin': (32, 36, 40), 'c4_slab': (512, 512, 1024)}
+    for name, shape in shapes.items():
+        with np.load(os.path.join(gdir, name + '.npz')) as z:
+            lattice, d, T, dV = z['lattice'], z['distance_matrix'], z['T_grad'], float(z['voxel_volume'])
+        np.testing.assert_array_equal(geo.distance_matrix(lattice, shape), d, err_msg=name)
+        np.testing.assert_array_equal(geo.T_grad(lattice, shape), T, err_msg=name)
+        assert geo.voxel_volume(lattice, shape) == dV, name
