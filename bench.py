@@ -392,7 +392,7 @@ def main():
     ap.add_argument('--ref-sample', type=int, default=160, help='port fallback: cell edge')
     ap.add_argument('--ref-spacing', type=float, default=0.0,
                     help='reference arm: atom spacing in voxels of its 2x2x2-atom cell (0: picked to fit --ref-budget)')
-    ap.add_argument('--ref-budget', type=float, default=200.0, help='reference arm: seconds for all steps')
+    ap.add_argument('--ref-budget', type=float, default=120.0, help='reference arm: seconds for all steps')
     ap.add_argument('--ref-port', action='store_true', help='reference arm / cpu baseline: force the C port')
     ap.add_argument('--halo', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
