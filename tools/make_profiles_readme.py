@@ -144,6 +144,7 @@ for f in sorted(os.listdir(P)):
             'sharded_handlers_w2_pytest.log': "first run of the unmodified `Bader.__call__` over 2 ranks",
             'trace_occupancy.txt': "A/B of k_trace launch bounds and refill chunk",
             'sanitizer_memcheck.log': "compute-sanitizer memcheck over smoke(): 0 errors",
+            'sanitizer_memcheck_parity.log': "compute-sanitizer memcheck over the vacuum / ragged parity cases: 0 errors",
             'sanitizer_racecheck.log': "compute-sanitizer racecheck over smoke(): the intended in-tile chase race only (DESIGN.md section 8)",
             'io_bench_256.json': "tools/io_bench.py: CHGCAR reader (GPU text -> grid) next to the reference's conversion"}
     desc = next((v for k, v in what.items() if f.endswith(k)), '')
