@@ -460,7 +460,7 @@ def main():
     clocks.start()
     e.profile(True)
     e.profile_reset()
-    l0 = e.launch_count()
+    l0, s0 = e.launch_count(), e.sync_count()
     e.synchronize()
     e.timer_start()
     for _ in range(args.steps):
@@ -468,6 +468,7 @@ def main():
     total_ms = e.timer_stop()
     e.synchronize()
     launches = e.launch_count() - l0
+    host_syncs = e.sync_count() - s0
     prof = e.profile_get()
     tsteps, tvox = e.trace_steps()
     e.profile(False)
@@ -547,6 +548,7 @@ def main():
                    "l2": "inputs (8 B/voxel density) are far larger than the 126 MB L2; no flush",
                    "parallelism": "1 GPU"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "host_syncs_per_step": host_syncs / args.steps,
         "clocks": clock_info, "kernels": kernels,
         "refine_history_last_step": hist,
     }

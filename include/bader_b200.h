@@ -165,6 +165,9 @@ int bdr_profile_reset(bdr_ctx *ctx);
 int bdr_profile_get(bdr_ctx *ctx, int family, double *ms, int64_t *launches);
 /* number of kernels this library launched on the handle since creation      */
 int bdr_launch_count(bdr_ctx *ctx, int64_t *launches);
+/* number of device-counter read-backs (host decisions between data-dependent launches,
+ * each a stream synchronisation) on the handle since creation                       */
+int bdr_sync_count(bdr_ctx *ctx, int64_t *syncs);
 /* CUDA-event stopwatch on the handle's stream (the stream every kernel of
  * this library is launched on): start records an event, stop records a second
  * one, synchronises and returns the elapsed milliseconds.                   */

@@ -47,6 +47,7 @@ SIGNATURES = {
     "bdr_profile_reset": ([_p], _int),
     "bdr_profile_get": ([_p, _int, ctypes.POINTER(_f64), ctypes.POINTER(_i64)], _int),
     "bdr_launch_count": ([_p, ctypes.POINTER(_i64)], _int),
+    "bdr_sync_count": ([_p, ctypes.POINTER(_i64)], _int),
     "bdr_timer_start": ([_p], _int),
     "bdr_timer_stop": ([_p, ctypes.POINTER(_f64)], _int),
     "bdr_trace_steps": ([_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)], _int),

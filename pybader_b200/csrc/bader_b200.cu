@@ -2375,6 +2375,11 @@ int bdr_launch_count(bdr_ctx *c, int64_t *launches) {
     *launches = c->launches;
     return 0;
 }
+int bdr_sync_count(bdr_ctx *c, int64_t *syncs) {
+    TRY(check(c));
+    *syncs = c->syncs;
+    return 0;
+}
 int bdr_timer_start(bdr_ctx *c) {
     TRY(check(c));
     if (!c->t0) {

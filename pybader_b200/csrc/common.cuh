@@ -187,6 +187,7 @@ struct bdr_ctx {
     double prof_ms[BDR_K_COUNT] = {0};
     int64_t prof_n[BDR_K_COUNT] = {0};
     int64_t launches = 0;
+    int64_t syncs = 0;            // counter read-backs (host decisions between data-dependent launches)
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int64_t trace_steps = 0, trace_voxels = 0;
     double dbg_upload_ms = 0;  // BDR_DEBUG: host->device upload + stencil of the last bdr_run
@@ -265,6 +266,7 @@ inline int ensure_stage(bdr_ctx *c, size_t bytes) {
 
 // read the device counters (synchronises the stream)
 inline int read_counters(bdr_ctx *c) {
+    c->syncs++;
     CU(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(unsigned long long) * CNT_NUM,
                        cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -201,6 +201,11 @@ class Engine:
         check(self.lib.bdr_launch_count(self.h, ctypes.byref(n)))
         return n.value
 
+    def sync_count(self):
+        n = ctypes.c_int64(0)
+        check(self.lib.bdr_sync_count(self.h, ctypes.byref(n)))
+        return n.value
+
     def timer_start(self):
         check(self.lib.bdr_timer_start(self.h))
 
