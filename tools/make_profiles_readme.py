@@ -60,7 +60,8 @@ for tagw, label in (('c3', 'BASELINE config 3'), ('c4', 'BASELINE config 4')):
         dw = load(f'{tag}_bench_{tagw}.json')
         w(f"| {label} (`bench.py --workload {tagw}`) | {dw['ms_per_step']:.2f} ms → {dw['value'] / 1e9:.2f} Gvoxel/s; e2e "
           f"{dw['e2e']['ms_per_step']:.1f} ms; {dw['config']['maxima']} maxima, refine history {dw['refine_history_last_step']} |")
-w(f"| kernels launched per step (`gpu_launches` / steps) | {b['gpu_launches'] / b['steps']:.0f} |")
+w(f"| kernels launched per step (`gpu_launches` / steps) | {b['gpu_launches'] / b['steps']:.0f}; host counter "
+  f"read-backs per step: {b.get('host_syncs_per_step', float('nan')):.0f} |")
 w(f"| SM clock during the timed region | {b['clocks']['sm_mhz']} MHz of {b['clocks']['sm_max_mhz']} (reasons: {b['clocks']['reasons'] or 'none'}) |")
 r = b['roofline']
 w(f"| `roofline` (dominant family: {r['kernel']}) | achieved {r['achieved']:.0f} GB/s algorithmic of {r['peak']:.0f} GB/s "
