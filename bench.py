@@ -12,11 +12,17 @@ i.e. thread_handlers.bader_calc + thread_handlers.refine of the reference
 `value`  = voxels / device time of the step, density already resident in HBM.
 `e2e`    = the same metric through the C ABI one-shot call `bdr_run` with HOST
            buffers: pinned-host density in, narrowed labels + maxima out, the
-           H2D / D2H copies inside the timed region.
-`roofline` is for the dominant streaming kernel family of the step, from CUDA
-events recorded on the library's own stream around every launch.
-`cpu_baseline` times the CPU oracle (a single-threaded C port of the
-reference's numba kernels) on a bounded sample of the same workload family.
+           H2D / D2H copies inside the timed region.  `e2e.handlers` is the same
+           step through the reference-shaped Python handlers (what the unmodified
+           `Bader` object drives) with pageable numpy arrays.
+`roofline` is for the family of kernels that takes the largest share of the
+step, from CUDA events recorded on the library's own stream around every launch.
+`cpu_baseline` / `--impl reference` time the UNMODIFIED reference (pybader's
+numba thread handlers from baseline/_ref, all host threads) on a bounded sample
+of the same workload family; only if pybader cannot be imported on the box the
+C port of its algorithm (oracle/) runs instead, and the line says so.
+`--workload c3|c4` measures BASELINE configs 3 and 4 instead of the 1024^3 target.
+N > 1 (under torchrun): pybader_b200.sharded.bench, weak scaling, 2^30 voxels per GPU.
 """
 import argparse
 import json
