@@ -173,6 +173,10 @@ def _bader_worker(rank, world, port, out):
         b = tb.make_bader(ref, {'charge': rho}, g)
         tb.compare(b, g, labels_exact=False)
         d1 = int(np.count_nonzero(b.bader_volumes != g['bader_volumes']))
+        # utils.volume_mask over the ranks (the export path, interface.py:600-621)
+        from pybader_b200 import utils as ut
+        m = ut.volume_mask(b.bader_volumes, rho, 1)
+        np.testing.assert_array_equal(m, np.where(b.bader_volumes == 1, rho, 0.0))
         # the `speed` profile: ongrid + refine ('changed', 3) on atoms_volumes, bit-exact
         g2 = tb.load('c1_speed')
         b2 = tb.make_bader(ref, {'charge': rho}, g2, profile='speed')
